@@ -1,0 +1,841 @@
+// capi.cu -- the extern "C" boundary (include/cyrk_b200.h): argument validation, device arena,
+// host<->device transfers, kernel dispatch, result handle.  No solver arithmetic lives here.
+//
+// Reference counterparts: CyRK/nb/numba_c_api_.cpp (flat API), CyRK/cy/cysolve.cpp:6-114
+// (config update -> setup -> solve), CyRK/cy/c_common.cpp:20-56 (max_num_steps from the RAM cap),
+// CyRK/cy/rk.cpp:578-608 (tolerance validation + rtol floor).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cyrk_b200.h"
+#include "cyrk_defs.h"
+#include "registry.h"
+#include "problems_builtin.cuh"
+#include "cta_solver.h"
+#include "nvrtc_rhs.h"
+
+namespace cyrk {
+
+// ------------------------------------------------------------------------------------------------
+// error reporting
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...)
+{
+    char buf[2048];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+#define CU_TRY(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, \
+                      cudaGetErrorString(e__));                                              \
+            return -1;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// registry
+// ------------------------------------------------------------------------------------------------
+static ProblemEntry g_table[FP_COUNT][RHS_TABLE_SIZE];
+ProblemEntry* registry_slot(int fp, int id) { return &g_table[fp][id]; }
+const ProblemEntry* registry_lookup(int fp, int id)
+{
+    if (fp < 0 || fp >= FP_COUNT || id < 0 || id >= RHS_TABLE_SIZE) return nullptr;
+    return g_table[fp][id].present ? &g_table[fp][id] : nullptr;
+}
+
+#define CYRK_DECL_REG(P) void cyrk_register_##P##_fast(); void cyrk_register_##P##_strict();
+#define CYRK_CALL_REG(P) cyrk_register_##P##_fast(); cyrk_register_##P##_strict();
+#define CYRK_ALL_PROBLEMS(X)                                                                       \
+    X(ProbBaseline) X(ProbAccuracy) X(ProbExtraOutput) X(ProbLorenz) X(ProbLorenzExtra)           \
+    X(ProbLotkaVolterra) X(ProbPendulum) X(ProbArbitraryArgs) X(ProbPendulumPreEval)              \
+    X(ProbPendulumDrag) X(ProbDenseKat)
+CYRK_ALL_PROBLEMS(CYRK_DECL_REG)
+
+void registry_init()
+{
+    static std::once_flag once;
+    std::call_once(once, [] { CYRK_ALL_PROBLEMS(CYRK_CALL_REG) });
+}
+
+// ------------------------------------------------------------------------------------------------
+// options
+// ------------------------------------------------------------------------------------------------
+static int g_opt_refill_min = 8;
+static int g_opt_block = 128;
+static int g_opt_ctas_per_sm = 0;
+
+// ------------------------------------------------------------------------------------------------
+// grow-only buffers
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            size_t fr = 0, tot = 0;
+            cudaMemGetInfo(&fr, &tot);
+            set_error("device allocation of %zu bytes failed (%s); %zu of %zu bytes free -- split the batch or "
+                      "lower expected_size / t_eval / dense_output storage", bytes, cudaGetErrorString(e), fr, tot);
+            cudaGetLastError();
+            return -1;
+        }
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+        if (e != cudaSuccess) {
+            set_error("pinned host allocation of %zu bytes failed (%s)", bytes, cudaGetErrorString(e));
+            cudaGetLastError();
+            return -1;
+        }
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// result handle
+// ------------------------------------------------------------------------------------------------
+struct Handle {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
+    // problem of the last solve
+    int rhs_id = -1, method = 0, fp_mode = 0;
+    size_t n_traj = 0, ny = 0, nx = 0, ndy = 0, q_order = 0;
+    size_t n_events = 0, n_t_eval = 0;
+    size_t row_cap = 0, dense_cap = 0, ev_cap = 0;
+    bool dense_output = false, device_io = false, solved = false;
+    size_t args_stride = 0;
+    // device arena
+    DevBuf d_y0, d_args, d_tspan, d_teval, d_queue;
+    DevBuf d_status, d_size, d_steps, d_nrej, d_nfev, d_tlast, d_ylast;
+    DevBuf d_trows, d_yrows, d_dense_t, d_dense_state, d_dense_count;
+    DevBuf d_ev_t, d_ev_y, d_ev_count, d_ev_term;
+    DevBuf d_q_t, d_q_out, d_q_code, d_scratch;
+    // pinned host mirrors
+    PinBuf h_status, h_size, h_steps, h_nrej, h_nfev, h_tlast, h_ylast;
+    PinBuf h_trows, h_yrows, h_dense_count, h_ev_t, h_ev_y, h_ev_count, h_ev_term;
+    PinBuf h_stage;
+    // device-pointer inputs in DEVICE_IO mode
+    const double* in_y0 = nullptr;
+    const char* in_args = nullptr;
+    const double* in_tspan = nullptr;
+    size_t tspan_stride = 0;
+    // stats
+    float kernel_ms = 0.f, total_ms = 0.f;
+    unsigned launches = 0;
+    size_t h2d_bytes = 0, d2h_bytes = 0;
+
+    int bind(int dev)
+    {
+        if (device == dev && stream) { CU_TRY(cudaSetDevice(dev)); return 0; }
+        if (stream) destroy_cuda();
+        CU_TRY(cudaSetDevice(dev));
+        CU_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreate(&ev_begin));
+        CU_TRY(cudaEventCreate(&ev_k0));
+        CU_TRY(cudaEventCreate(&ev_k1));
+        CU_TRY(cudaEventCreate(&ev_end));
+        device = dev;
+        return 0;
+    }
+    void destroy_cuda()
+    {
+        if (device >= 0) cudaSetDevice(device);
+        DevBuf* dbs[] = {&d_y0, &d_args, &d_tspan, &d_teval, &d_queue, &d_status, &d_size, &d_steps, &d_nrej, &d_nfev,
+                         &d_tlast, &d_ylast, &d_trows, &d_yrows, &d_dense_t, &d_dense_state, &d_dense_count, &d_ev_t,
+                         &d_ev_y, &d_ev_count, &d_ev_term, &d_q_t, &d_q_out, &d_q_code, &d_scratch};
+        for (DevBuf* b : dbs) b->release();
+        PinBuf* pbs[] = {&h_status, &h_size, &h_steps, &h_nrej, &h_nfev, &h_tlast, &h_ylast, &h_trows, &h_yrows,
+                         &h_dense_count, &h_ev_t, &h_ev_y, &h_ev_count, &h_ev_term, &h_stage};
+        for (PinBuf* b : pbs) b->release();
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_k0) cudaEventDestroy(ev_k0);
+        if (ev_k1) cudaEventDestroy(ev_k1);
+        if (ev_end) cudaEventDestroy(ev_end);
+        if (stream) cudaStreamDestroy(stream);
+        ev_begin = ev_k0 = ev_k1 = ev_end = nullptr;
+        stream = nullptr;
+        device = -1;
+    }
+    ~Handle() { destroy_cuda(); }
+};
+
+// cy/c_common.cpp:20-56
+static void find_max_num_steps(size_t ny, size_t nx, size_t user, size_t ram_MB, int* user_flag, size_t* out)
+{
+    const double ram = ram_MB * (1000.0 * 1000.0) / (sizeof(double) * (1.0 + ny + nx));
+    const size_t ram_steps = (size_t)std::floor(ram);
+    *user_flag = 0;
+    *out = ram_steps;
+    if (user > 0) {
+        if (user > ram_steps) *out = ram_steps;
+        else { *user_flag = 1; *out = user; }
+    }
+    if (*out > (SIZE_MAX / 10)) *out = SIZE_MAX / 10;
+}
+
+struct SolveArgs {
+    int rhs_id, method;
+    size_t n_traj;
+    const double* t_span; size_t n_t_span;
+    const double* y0; size_t n_y;
+    size_t num_extra;
+    const char* args; size_t args_len, n_args;
+    size_t max_num_steps, max_ram_MB;
+    int dense_output;
+    const double* t_eval; size_t n_t_eval;
+    const int* event_ids; const int* event_dirs; const size_t* event_max; size_t n_events;
+    const double* rtols; size_t n_rtols;
+    const double* atols; size_t n_atols;
+    double max_step, first_step;
+    size_t expected_size;
+    int store_mode; unsigned flags; int device;
+};
+
+static int upload(Handle* h, DevBuf& dst, const void* src, size_t bytes)
+{
+    if (dst.ensure(bytes ? bytes : 8)) return -1;
+    if (bytes) {
+        CU_TRY(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        h->h2d_bytes += bytes;
+    }
+    return 0;
+}
+
+static int download(Handle* h, PinBuf& dst, const DevBuf& src, size_t bytes)
+{
+    if (dst.ensure(bytes)) return -1;
+    if (bytes) {
+        CU_TRY(cudaMemcpyAsync(dst.p, src.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+        h->d2h_bytes += bytes;
+    }
+    return 0;
+}
+
+static int device_sm_count(int dev)
+{
+    static int cache[64];
+    if (dev < 64 && cache[dev]) return cache[dev];
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (dev < 64) cache[dev] = n;
+    return n;
+}
+
+// The thread-per-trajectory path.  Returns 0 / -1.
+static int solve_thread_path(Handle* h, const SolveArgs& a, const ProblemEntry* pe)
+{
+    const size_t B = a.n_traj, NY = pe->ny, NX = pe->nextra, NDY = NY + NX;
+    const bool device_io = (a.flags & CYRK_FLAG_DEVICE_IO) != 0;
+    const bool want_rows = a.store_mode == CYRK_STORE_ROWS;
+    const bool dense = a.dense_output != 0;
+    const int variant = (dense || a.n_events > 0) ? VAR_FULL : ((want_rows || a.n_t_eval > 0) ? VAR_ROWS : VAR_LEAN);
+    const KernelEntry& ke = pe->solve[a.method - 3][variant];
+    const int q_order = a.method == CYRK_METHOD_RK23 ? 3 : a.method == CYRK_METHOD_RK45 ? 4 : 7;
+
+    h->ny = NY; h->nx = NX; h->ndy = NDY; h->q_order = q_order;
+    h->n_traj = B; h->n_events = a.n_events; h->n_t_eval = a.n_t_eval;
+    h->dense_output = dense; h->device_io = device_io;
+    h->h2d_bytes = h->d2h_bytes = 0; h->launches = 0; h->kernel_ms = 0.f;
+
+    BatchParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_traj = B;
+    for (size_t i = 0; i < NY; i++) {
+        double r = a.rtols[a.n_rtols > 1 ? i : 0];
+        if (r < 100.0 * std::numeric_limits<double>::epsilon()) r = 100.0 * std::numeric_limits<double>::epsilon();
+        p.rtol[i] = r;
+        p.atol[i] = a.atols[a.n_atols > 1 ? i : 0];
+    }
+    p.max_step = a.max_step;
+    p.first_step = a.first_step;
+    {
+        int uf; size_t mx;
+        find_max_num_steps(NY, NX, a.max_num_steps, a.max_ram_MB, &uf, &mx);
+        p.user_max_steps = uf;
+        p.max_num_steps = (unsigned)std::min<size_t>(mx, 0xffffffffu);
+    }
+    p.dense_output = dense ? 1 : 0;
+    p.n_events = (int)a.n_events;
+    for (size_t e = 0; e < a.n_events; e++) {
+        p.ev_id[e] = a.event_ids[e];
+        p.ev_dir[e] = a.event_dirs ? a.event_dirs[e] : 0;
+        p.ev_max[e] = a.event_max ? (unsigned long long)a.event_max[e] : ~0ull;
+    }
+    p.refill_min = std::min(32, std::max(1, g_opt_refill_min));
+
+    CU_TRY(cudaEventRecord(h->ev_begin, h->stream));
+
+    // ---- inputs
+    const size_t args_stride = (size_t)pe->nargs_dbl * sizeof(double);
+    if (device_io) {
+        p.y0 = a.y0;
+        p.args = a.args;
+        p.args_stride = a.n_args > 1 ? (unsigned)args_stride : 0u;
+        if (a.args_len != args_stride && pe->nargs_dbl > 0) {
+            set_error("CYRK_FLAG_DEVICE_IO requires args blobs of exactly %zu bytes for this right-hand side (got %zu)",
+                      args_stride, a.args_len);
+            return -1;
+        }
+        p.t_span = a.t_span;
+        p.t_span_stride = a.n_t_span > 1 ? 2u : 0u;
+    } else {
+        if (upload(h, h->d_y0, a.y0, B * NY * sizeof(double))) return -1;
+        p.y0 = h->d_y0.as<double>();
+        // args: zero-pad every blob to the functor's size
+        const size_t n_blobs = a.n_args > 1 ? B : 1;
+        if (pe->nargs_dbl > 0) {
+            if (a.args_len == args_stride && a.n_args >= 1) {
+                if (upload(h, h->d_args, a.args, n_blobs * args_stride)) return -1;
+            } else {
+                if (h->h_stage.ensure(n_blobs * args_stride)) return -1;
+                char* st = h->h_stage.as<char>();
+                memset(st, 0, n_blobs * args_stride);
+                if (a.n_args >= 1)
+                    for (size_t i = 0; i < n_blobs; i++) memcpy(st + i * args_stride, a.args + i * a.args_len, a.args_len);
+                if (upload(h, h->d_args, st, n_blobs * args_stride)) return -1;
+            }
+        } else {
+            if (h->d_args.ensure(8)) return -1;
+        }
+        p.args = h->d_args.as<char>();
+        p.args_stride = a.n_args > 1 ? (unsigned)args_stride : 0u;
+        if (upload(h, h->d_tspan, a.t_span, a.n_t_span * 2 * sizeof(double))) return -1;
+        p.t_span = h->d_tspan.as<double>();
+        p.t_span_stride = a.n_t_span > 1 ? 2u : 0u;
+    }
+    h->in_y0 = p.y0; h->in_args = p.args; h->in_tspan = p.t_span;
+    h->tspan_stride = p.t_span_stride; h->args_stride = p.args_stride;
+
+    // t_eval: always a host pointer (small, shared).  Backward runs search the reversed copy
+    // (cysolver.cpp:381-400).
+    std::vector<double> te;
+    if (a.n_t_eval) {
+        te.assign(a.t_eval, a.t_eval + a.n_t_eval);
+        bool fwd0;
+        if (device_io) {
+            double ts0[2];
+            CU_TRY(cudaMemcpyAsync(ts0, a.t_span, sizeof(ts0), cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            fwd0 = (ts0[1] - ts0[0]) >= 0.0;
+        } else {
+            fwd0 = (a.t_span[1] - a.t_span[0]) >= 0.0;
+            if (a.n_t_span > 1) {
+                for (size_t i = 1; i < B; i++)
+                    if (((a.t_span[2 * i + 1] - a.t_span[2 * i]) >= 0.0) != fwd0) {
+                        set_error("t_eval is shared by the batch: every t_span must integrate in the same direction");
+                        return -1;
+                    }
+            }
+        }
+        if (!fwd0) std::reverse(te.begin(), te.end());
+        if (h->d_teval.ensure(te.size() * sizeof(double))) return -1;
+        // synchronous on purpose: `te` is a stack-owned temporary
+        CU_TRY(cudaMemcpyAsync(h->d_teval.p, te.data(), te.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        h->h2d_bytes += te.size() * sizeof(double);
+        p.t_eval = h->d_teval.as<double>();
+        p.n_t_eval = (unsigned)a.n_t_eval;
+    }
+
+    // ---- per-trajectory outputs
+    if (h->d_status.ensure(B * 4) || h->d_size.ensure(B * 4) || h->d_steps.ensure(B * 4) || h->d_nrej.ensure(B * 4) ||
+        h->d_nfev.ensure(B * 4) || h->d_tlast.ensure(B * 8) || h->d_ylast.ensure(B * NDY * 8) || h->d_queue.ensure(8))
+        return -1;
+    p.status = h->d_status.as<int>();
+    p.size = h->d_size.as<unsigned>();
+    p.steps_taken = h->d_steps.as<unsigned>();
+    p.n_rejected = h->d_nrej.as<unsigned>();
+    p.nfev = h->d_nfev.as<unsigned>();
+    p.t_last = h->d_tlast.as<double>();
+    p.y_last = h->d_ylast.as<double>();
+    p.queue = h->d_queue.as<unsigned long long>();
+
+    size_t row_cap = 0, dense_cap = 0, ev_cap = 0;
+    if (want_rows) row_cap = a.n_t_eval ? a.n_t_eval : (a.expected_size ? a.expected_size : 256);
+    if (dense) dense_cap = a.expected_size ? a.expected_size + 1 : 257;
+    if (a.n_events) ev_cap = a.expected_size ? a.expected_size : 64;
+
+    int grid = 0;
+    {
+        int ctas = g_opt_ctas_per_sm;
+        if (ctas <= 0) {
+            CU_TRY(ke.occupancy(&ctas, g_opt_block));
+            if (ctas <= 0) { set_error("kernel %s cannot be resident with %d threads per CTA", ke.name, g_opt_block); return -1; }
+        }
+        grid = device_sm_count(h->device) * ctas;
+        const unsigned long long need = (B + g_opt_block - 1) / g_opt_block;
+        if ((unsigned long long)grid > need) grid = (int)std::max<unsigned long long>(need, 1);
+    }
+
+    for (int pass = 0; pass < 2; pass++) {
+        if (want_rows) {
+            if (h->d_trows.ensure(B * row_cap * 8) || h->d_yrows.ensure(B * row_cap * NDY * 8)) return -1;
+            p.t_rows = h->d_trows.as<double>();
+            p.y_rows = h->d_yrows.as<double>();
+            p.row_cap = (unsigned)row_cap;
+        }
+        if (dense) {
+            if (h->d_dense_t.ensure(B * dense_cap * 8) ||
+                h->d_dense_state.ensure(B * dense_cap * NY * (q_order + 1) * 8) || h->d_dense_count.ensure(B * 4))
+                return -1;
+            p.dense_t = h->d_dense_t.as<double>();
+            p.dense_state = h->d_dense_state.as<double>();
+            p.dense_count = h->d_dense_count.as<unsigned>();
+            p.dense_cap = (unsigned)dense_cap;
+        }
+        if (a.n_events) {
+            if (h->d_ev_t.ensure(B * a.n_events * ev_cap * 8) || h->d_ev_y.ensure(B * a.n_events * ev_cap * NDY * 8) ||
+                h->d_ev_count.ensure(B * a.n_events * 4) || h->d_ev_term.ensure(B * 4))
+                return -1;
+            p.ev_t = h->d_ev_t.as<double>();
+            p.ev_y = h->d_ev_y.as<double>();
+            p.ev_count = h->d_ev_count.as<unsigned>();
+            p.ev_term_index = h->d_ev_term.as<int>();
+            p.ev_cap = (unsigned)ev_cap;
+        }
+        CU_TRY(cudaMemsetAsync(h->d_queue.p, 0, 8, h->stream));
+        CU_TRY(cudaEventRecord(pass == 0 ? h->ev_k0 : h->ev_k0, h->stream));
+        CU_TRY(ke.launch(p, grid, g_opt_block, h->stream));
+        h->launches++;
+        CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
+
+        // counters come back first: they decide whether any arena overflowed
+        if (download(h, h->h_size, h->d_size, B * 4)) return -1;
+        if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
+        if (a.n_events && download(h, h->h_ev_count, h->d_ev_count, B * a.n_events * 4)) return -1;
+        bool need_check = want_rows || dense || a.n_events;
+        if (!need_check) break;
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1);
+            h->kernel_ms += ms;
+        }
+        size_t mx_rows = 0, mx_dense = 0, mx_ev = 0;
+        if (want_rows) { const unsigned* s = h->h_size.as<unsigned>(); for (size_t i = 0; i < B; i++) mx_rows = std::max<size_t>(mx_rows, s[i]); }
+        if (dense) { const unsigned* s = h->h_dense_count.as<unsigned>(); for (size_t i = 0; i < B; i++) mx_dense = std::max<size_t>(mx_dense, s[i]); }
+        if (a.n_events) { const unsigned* s = h->h_ev_count.as<unsigned>(); for (size_t i = 0; i < B * a.n_events; i++) mx_ev = std::max<size_t>(mx_ev, s[i]); }
+        const bool overflow = mx_rows > row_cap || mx_dense > dense_cap || mx_ev > ev_cap;
+        if (!overflow) break;
+        if (pass == 1) { set_error("internal: arena overflow after the exact-capacity re-run"); return -1; }
+        // deterministic re-run with exact capacities
+        row_cap = std::max(row_cap, mx_rows);
+        dense_cap = std::max(dense_cap, mx_dense);
+        ev_cap = std::max(ev_cap, mx_ev);
+    }
+    h->row_cap = row_cap; h->dense_cap = dense_cap; h->ev_cap = ev_cap;
+
+    // ---- results to the host
+    if (!device_io) {
+        if (download(h, h->h_status, h->d_status, B * 4) || download(h, h->h_steps, h->d_steps, B * 4) ||
+            download(h, h->h_nrej, h->d_nrej, B * 4) || download(h, h->h_nfev, h->d_nfev, B * 4) ||
+            download(h, h->h_tlast, h->d_tlast, B * 8) || download(h, h->h_ylast, h->d_ylast, B * NDY * 8))
+            return -1;
+        if (want_rows) {
+            if (download(h, h->h_trows, h->d_trows, B * row_cap * 8) || download(h, h->h_yrows, h->d_yrows, B * row_cap * NDY * 8))
+                return -1;
+        }
+        if (a.n_events) {
+            if (download(h, h->h_ev_t, h->d_ev_t, B * a.n_events * ev_cap * 8) ||
+                download(h, h->h_ev_y, h->d_ev_y, B * a.n_events * ev_cap * NDY * 8) ||
+                download(h, h->h_ev_term, h->d_ev_term, B * 4))
+                return -1;
+        }
+    }
+    CU_TRY(cudaEventRecord(h->ev_end, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (!(want_rows || dense || a.n_events)) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1);
+        h->kernel_ms = ms;
+    }
+    cudaEventElapsedTime(&h->total_ms, h->ev_begin, h->ev_end);
+    return 0;
+}
+
+static int validate(const SolveArgs& a)
+{
+    if (a.n_traj == 0) { set_error("n_traj must be > 0"); return -1; }
+    if (a.method < CYRK_METHOD_RK23 || a.method > CYRK_METHOD_DOP853) {
+        set_error("unknown or unsupported integration method %d (supported: RK23=3, RK45=4, DOP853=5)", a.method);
+        return -1;
+    }
+    if (!a.y0 || a.n_y == 0) { set_error("y0 is required and n_y must be > 0"); return -1; }
+    if (!a.t_span || !(a.n_t_span == 1 || a.n_t_span == a.n_traj)) { set_error("t_span must hold 1 or n_traj (t_start, t_end) pairs"); return -1; }
+    if (!a.rtols || !a.atols || a.n_rtols == 0 || a.n_atols == 0 || (a.n_rtols > 1 && a.n_rtols != a.n_y) ||
+        (a.n_atols > 1 && a.n_atols != a.n_y)) {
+        set_error("rtols/atols must have 1 or n_y entries (CyrkErrorCodes::BAD_CONFIG_DATA, -22)");
+        return -1;
+    }
+    if (!(a.n_args == 0 || a.n_args == 1 || a.n_args == a.n_traj)) { set_error("n_args must be 0, 1 or n_traj"); return -1; }
+    if (a.n_args > 0 && a.args_len > 0 && !a.args) { set_error("args pointer is NULL"); return -1; }
+    if (a.n_events > CYRK_MAX_EVENTS) { set_error("at most %d events are supported", CYRK_MAX_EVENTS); return -1; }
+    if (a.n_events && !a.event_ids) { set_error("event_ids is NULL"); return -1; }
+    if (a.n_t_eval && !a.t_eval) { set_error("t_eval is NULL"); return -1; }
+    if (a.store_mode != CYRK_STORE_FINAL && a.store_mode != CYRK_STORE_ROWS) { set_error("unknown store_mode %d", a.store_mode); return -1; }
+    if (a.max_step < 0.0) { set_error("max_step must be positive"); return -1; }
+    return 0;
+}
+
+static int solve_impl(Handle* h, const SolveArgs& a)
+{
+    h->solved = false;
+    if (validate(a)) return -1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: cyrk_b200 has no CPU fallback");
+        return -1;
+    }
+    if (a.device < 0 || a.device >= ndev) { set_error("device %d out of range (%d devices)", a.device, ndev); return -1; }
+    if (h->bind(a.device)) return -1;
+    registry_init();
+    const int fp = (a.flags & CYRK_FLAG_STRICT_FP) ? FP_STRICT : FP_FAST;
+    h->rhs_id = a.rhs_id; h->method = a.method; h->fp_mode = fp;
+
+    if (a.rhs_id == CYRK_RHS_LARGEY || a.rhs_id == CYRK_RHS_LARGEY_SIMPLE) {
+        set_error("CTA-per-trajectory path not built yet");
+        return -1;
+    }
+    if (a.rhs_id >= CYRK_RHS_USER_BASE) {
+        set_error("NVRTC user right-hand sides not built yet");
+        return -1;
+    }
+    const ProblemEntry* pe = registry_lookup(fp, a.rhs_id);
+    if (!pe) { set_error("unknown right-hand side id %d", a.rhs_id); return -1; }
+    if ((size_t)pe->ny != a.n_y) { set_error("right-hand side %d has n_y = %d but y0 has n_y = %zu", a.rhs_id, pe->ny, a.n_y); return -1; }
+    if ((size_t)pe->nextra != a.num_extra) {
+        set_error("right-hand side %d produces %d extra outputs but num_extra = %zu", a.rhs_id, pe->nextra, a.num_extra);
+        return -1;
+    }
+    if (a.n_args > 0 && a.args_len > (size_t)pe->nargs_dbl * 8) {
+        set_error("args blob of %zu bytes exceeds the %d bytes right-hand side %d reads", a.args_len, pe->nargs_dbl * 8, a.rhs_id);
+        return -1;
+    }
+    for (size_t e = 0; e < a.n_events; e++)
+        if (a.event_ids[e] < 0 || a.event_ids[e] >= EV_TABLE_SIZE) { set_error("unknown event id %d", a.event_ids[e]); return -1; }
+    if (solve_thread_path(h, a, pe)) return -1;
+    h->solved = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 throughput probe: 8 independent DFMA chains per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void fp64_probe_kernel(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace cyrk
+
+using namespace cyrk;
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+extern "C" {
+
+int cyrk_b200_version(void) { return 100; }
+
+int cyrk_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* cyrk_b200_last_error(void) { return g_last_error.c_str(); }
+
+void cyrk_b200_status_message(int code, char* buffer, size_t max_len)
+{
+    // message table of CyRK/cy/c_common.hpp:84-177
+    const char* m = "UNKNOWN_ERROR";
+    switch (code) {
+    case 20: m = "An optimization routine has successfully converged."; break;
+    case 10: m = "Initializing. If you see this message then it was likely interrupted."; break;
+    case 2: m = "Integration ended early: An event has been triggered the maximum allowed times. No issues detected."; break;
+    case 1: m = "Integration completed without issue."; break;
+    case 0: m = "No errors were encountered."; break;
+    case -1: m = "An unspecified error has occurred."; break;
+    case -2: m = "A required property was not set."; break;
+    case -3: m = "The provided model is currently unsupported or not known."; break;
+    case -4: m = "A class object was not fully initialized."; break;
+    case -5: m = "Error in CySolver initialization."; break;
+    case -6: m = "The provided input is incompatible with other input or the current object(s) state."; break;
+    case -7: m = "Error when accessing or modifying one or more attributes/properties."; break;
+    case -8: m = "A bounds error was encountered."; break;
+    case -9: m = "A required function or method argument was not set."; break;
+    case -20: m = "An object's additional setup function was not called before its methods were used."; break;
+    case -21: m = "Can't call solution: Dense output was not saved."; break;
+    case -22: m = "Error during setup: Provided configuration data does not make sense or is missing required parameters."; break;
+    case -41: m = "A C++ vector object's size exceeds limits imposed by user or architecture."; break;
+    case -40: m = "There was an error while allocating memory."; break;
+    case -50: m = "The number of dependent `y` values is 0. There are no differential equations to solve."; break;
+    case -51: m = "The maximum number of iterations was hit."; break;
+    case -52: m = "Maximum number of steps (set by user) exceeded during integration."; break;
+    case -53: m = "Maximum number of steps (set by system architecture) exceeded during integration."; break;
+    case -54: m = "Error in step size calculation: Required step size is less than spacing between numbers."; break;
+    case -55: m = "Error in step size calculation: Error in step size acceptance."; break;
+    case -56: m = "Error during dense output build."; break;
+    case -57: m = "Can't call solution: Integration has not been completed or it was unsuccessful."; break;
+    case -70: m = "There was an error in the C++ backend when trying to import the required Python module."; break;
+    case -80: m = "User-provided initial step size must be a positive number."; break;
+    case -99: m = "An unknown error occurred."; break;
+    case -100: m = "The error code was never set."; break;
+    default: break;
+    }
+    if (!buffer || max_len == 0) return;
+    strncpy(buffer, m, max_len - 1);
+    buffer[max_len - 1] = '\0';
+}
+
+static const struct { const char* name; int id; } k_builtin_names[] = {
+    {"baseline", CYRK_RHS_BASELINE}, {"accuracy", CYRK_RHS_ACCURACY}, {"extraoutput", CYRK_RHS_EXTRAOUTPUT},
+    {"lorenz", CYRK_RHS_LORENZ}, {"lorenz_extraoutput", CYRK_RHS_LORENZ_EXTRA}, {"lotkavolterra", CYRK_RHS_LOTKAVOLTERRA},
+    {"pendulum", CYRK_RHS_PENDULUM}, {"arbitrary_args", CYRK_RHS_ARBITRARY_ARGS}, {"pendulum_preeval", CYRK_RHS_PENDULUM_PREEVAL},
+    {"largey", CYRK_RHS_LARGEY}, {"largey_simple", CYRK_RHS_LARGEY_SIMPLE}, {"pendulum_drag", CYRK_RHS_PENDULUM_DRAG},
+    {"dense_kat", CYRK_RHS_DENSE_KAT}};
+
+int cyrk_b200_rhs_builtin(const char* name)
+{
+    if (!name) return -1;
+    for (const auto& e : k_builtin_names)
+        if (strcmp(e.name, name) == 0) return e.id;
+    set_error("unknown built-in right-hand side '%s'", name);
+    return -1;
+}
+
+int cyrk_b200_rhs_info(int rhs_id, size_t* n_y, size_t* n_extra, size_t* args_bytes)
+{
+    registry_init();
+    if (rhs_id == CYRK_RHS_LARGEY || rhs_id == CYRK_RHS_LARGEY_SIMPLE) {
+        if (n_y) *n_y = 0;
+        if (n_extra) *n_extra = 0;
+        if (args_bytes) *args_bytes = 16;
+        return 0;
+    }
+    const ProblemEntry* pe = registry_lookup(FP_FAST, rhs_id);
+    if (!pe) { set_error("unknown right-hand side id %d", rhs_id); return -1; }
+    if (n_y) *n_y = pe->ny;
+    if (n_extra) *n_extra = pe->nextra;
+    if (args_bytes) *args_bytes = (size_t)pe->nargs_dbl * 8;
+    return 0;
+}
+
+int cyrk_b200_rhs_compile(const char*, const char*, size_t, size_t, size_t, size_t, char* log, size_t log_len)
+{
+    if (log && log_len) snprintf(log, log_len, "NVRTC path not built yet");
+    set_error("NVRTC path not built yet");
+    return -1;
+}
+
+void* cyrk_b200_result_create(void) { return new Handle(); }
+
+void cyrk_b200_free(void* h) { delete static_cast<Handle*>(h); }
+
+int cyrk_b200_solve_batch_noreturn(
+    void* handle, int rhs_id, int method, size_t n_traj, const double* t_span, size_t n_t_span, const double* y0,
+    size_t n_y, size_t num_extra, const char* args, size_t args_len, size_t n_args, size_t max_num_steps,
+    size_t max_ram_MB, int dense_output, const double* t_eval, size_t n_t_eval, const int* event_ids,
+    const int* event_dirs, const size_t* event_max, size_t n_events, const double* rtols, size_t n_rtols,
+    const double* atols, size_t n_atols, double max_step, double first_step, size_t expected_size, int store_mode,
+    unsigned flags, int device)
+{
+    if (!handle) { set_error("handle is NULL"); return -1; }
+    SolveArgs a{rhs_id, method, n_traj, t_span, n_t_span, y0, n_y, num_extra, args, args_len, n_args, max_num_steps,
+                max_ram_MB, dense_output, t_eval, n_t_eval, event_ids, event_dirs, event_max, n_events, rtols, n_rtols,
+                atols, n_atols, max_step, first_step, expected_size, store_mode, flags, device};
+    return solve_impl(static_cast<Handle*>(handle), a);
+}
+
+void* cyrk_b200_solve_batch(
+    int rhs_id, int method, size_t n_traj, const double* t_span, size_t n_t_span, const double* y0, size_t n_y,
+    size_t num_extra, const char* args, size_t args_len, size_t n_args, size_t max_num_steps, size_t max_ram_MB,
+    int dense_output, const double* t_eval, size_t n_t_eval, const int* event_ids, const int* event_dirs,
+    const size_t* event_max, size_t n_events, const double* rtols, size_t n_rtols, const double* atols, size_t n_atols,
+    double max_step, double first_step, size_t expected_size, int store_mode, unsigned flags, int device)
+{
+    Handle* h = new Handle();
+    if (cyrk_b200_solve_batch_noreturn(h, rhs_id, method, n_traj, t_span, n_t_span, y0, n_y, num_extra, args, args_len,
+                                       n_args, max_num_steps, max_ram_MB, dense_output, t_eval, n_t_eval, event_ids,
+                                       event_dirs, event_max, n_events, rtols, n_rtols, atols, n_atols, max_step,
+                                       first_step, expected_size, store_mode, flags, device)) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+#define H(h) (static_cast<Handle*>(h))
+#define PICK(h, dev, host, T) (H(h)->device_io ? static_cast<const T*>(H(h)->dev.p) : static_cast<const T*>(H(h)->host.p))
+size_t cyrk_b200_get_n_traj(void* h) { return H(h)->n_traj; }
+size_t cyrk_b200_get_num_y(void* h) { return H(h)->ny; }
+size_t cyrk_b200_get_num_dy(void* h) { return H(h)->ndy; }
+const int32_t* cyrk_b200_get_status_ptr(void* h) { return PICK(h, d_status, h_status, int32_t); }
+const uint32_t* cyrk_b200_get_size_ptr(void* h) { return PICK(h, d_size, h_size, uint32_t); }
+const uint32_t* cyrk_b200_get_steps_taken_ptr(void* h) { return PICK(h, d_steps, h_steps, uint32_t); }
+const uint32_t* cyrk_b200_get_n_rejected_ptr(void* h) { return PICK(h, d_nrej, h_nrej, uint32_t); }
+const uint32_t* cyrk_b200_get_nfev_ptr(void* h) { return PICK(h, d_nfev, h_nfev, uint32_t); }
+const double* cyrk_b200_get_t_last_ptr(void* h) { return PICK(h, d_tlast, h_tlast, double); }
+const double* cyrk_b200_get_y_last_ptr(void* h) { return PICK(h, d_ylast, h_ylast, double); }
+size_t cyrk_b200_get_row_capacity(void* h) { return H(h)->row_cap; }
+const double* cyrk_b200_get_t_ptr(void* h) { return H(h)->row_cap ? PICK(h, d_trows, h_trows, double) : nullptr; }
+const double* cyrk_b200_get_y_ptr(void* h) { return H(h)->row_cap ? PICK(h, d_yrows, h_yrows, double) : nullptr; }
+size_t cyrk_b200_get_num_events(void* h) { return H(h)->n_events; }
+size_t cyrk_b200_get_event_capacity(void* h) { return H(h)->ev_cap; }
+const uint32_t* cyrk_b200_get_event_count_ptr(void* h) { return H(h)->n_events ? PICK(h, d_ev_count, h_ev_count, uint32_t) : nullptr; }
+const double* cyrk_b200_get_event_t_ptr(void* h) { return H(h)->n_events ? PICK(h, d_ev_t, h_ev_t, double) : nullptr; }
+const double* cyrk_b200_get_event_y_ptr(void* h) { return H(h)->n_events ? PICK(h, d_ev_y, h_ev_y, double) : nullptr; }
+const int32_t* cyrk_b200_get_event_terminate_index_ptr(void* h) { return H(h)->n_events ? PICK(h, d_ev_term, h_ev_term, int32_t) : nullptr; }
+size_t cyrk_b200_get_num_interpolates_capacity(void* h) { return H(h)->dense_cap; }
+const uint32_t* cyrk_b200_get_num_interpolates_ptr(void* h) { return H(h)->dense_output ? PICK(h, d_dense_count, h_dense_count, uint32_t) : nullptr; }
+
+int cyrk_b200_call_vectorize(void* hv, const double* t, size_t n_t, double* out, int32_t* codes)
+{
+    Handle* h = H(hv);
+    if (!h || !h->solved) { set_error("handle holds no solution"); return -1; }
+    if (!t || !out || !codes || n_t == 0) { set_error("t, out and codes are required"); return -1; }
+    CU_TRY(cudaSetDevice(h->device));
+    const size_t B = h->n_traj, NDY = h->ndy;
+    if (!h->dense_output) {
+        // CySolverResult::call: -57 when the trajectory did not succeed, else -21 (cysolution.cpp:513-520)
+        std::vector<int32_t> st(B);
+        if (h->device_io) {
+            CU_TRY(cudaMemcpy(st.data(), h->d_status.p, B * 4, cudaMemcpyDeviceToHost));
+        } else {
+            memcpy(st.data(), h->h_status.p, B * 4);
+        }
+        for (size_t i = 0; i < B; i++) st[i] = (st[i] == 1 || st[i] == 2) ? ST_DENSE_OUTPUT_NOT_SAVED : ST_INTEGRATION_NOT_SUCCESSFUL;
+        if (h->device_io) { CU_TRY(cudaMemcpy(codes, st.data(), B * 4, cudaMemcpyHostToDevice)); }
+        else memcpy(codes, st.data(), B * 4);
+        return 0;
+    }
+    const ProblemEntry* pe = registry_lookup(h->fp_mode, h->rhs_id);
+    if (!pe) { set_error("dense evaluation is not available for right-hand side %d", h->rhs_id); return -1; }
+    DenseEvalParams q;
+    memset(&q, 0, sizeof(q));
+    q.n_traj = B;
+    q.n_query = (unsigned)n_t;
+    if (h->d_q_t.ensure(n_t * 8) || h->d_q_code.ensure(B * 4)) return -1;
+    CU_TRY(cudaMemcpyAsync(h->d_q_t.p, t, n_t * 8, h->device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    q.t_query = h->d_q_t.as<double>();
+    q.t_span = h->in_tspan;
+    q.t_span_stride = (unsigned)h->tspan_stride;
+    q.status = h->d_status.as<int>();
+    q.dense_t = h->d_dense_t.as<double>();
+    q.dense_state = h->d_dense_state.as<double>();
+    q.dense_count = h->d_dense_count.as<unsigned>();
+    q.dense_cap = (unsigned)h->dense_cap;
+    q.args = h->in_args;
+    q.args_stride = (unsigned)h->args_stride;
+    double* d_out;
+    if (h->device_io) d_out = out;
+    else {
+        if (h->d_q_out.ensure(B * n_t * NDY * 8)) return -1;
+        d_out = h->d_q_out.as<double>();
+    }
+    q.out = d_out;
+    q.code = h->device_io ? codes : h->d_q_code.as<int>();
+    CU_TRY(cudaMemsetAsync(q.code, 0, B * 4, h->stream));
+    const unsigned long long total = (unsigned long long)B * n_t;
+    const int block = 256;
+    const unsigned long long grid = (total + block - 1) / block;
+    if (grid > 0x7fffffffull) { set_error("too many query points"); return -1; }
+    CU_TRY(pe->dense_eval[h->method - 3](q, (int)grid, block, h->stream));
+    if (!h->device_io) {
+        CU_TRY(cudaMemcpyAsync(out, d_out, B * n_t * NDY * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaMemcpyAsync(codes, q.code, B * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+double cyrk_b200_get_kernel_ms(void* h) { return H(h)->kernel_ms; }
+double cyrk_b200_get_total_ms(void* h) { return H(h)->total_ms; }
+unsigned cyrk_b200_get_launch_count(void* h) { return H(h)->launches; }
+size_t cyrk_b200_get_h2d_bytes(void* h) { return H(h)->h2d_bytes; }
+size_t cyrk_b200_get_d2h_bytes(void* h) { return H(h)->d2h_bytes; }
+
+int cyrk_b200_set_option(const char* name, int value)
+{
+    if (!name) return -1;
+    if (!strcmp(name, "refill_min")) { g_opt_refill_min = value; return 0; }
+    if (!strcmp(name, "block")) { if (value < 32 || value > 1024 || value % 32) { set_error("block must be a multiple of 32 in [32,1024]"); return -1; } g_opt_block = value; return 0; }
+    if (!strcmp(name, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }
+    set_error("unknown option '%s'", name);
+    return -1;
+}
+
+double cyrk_b200_measure_fp64_tflops(int device)
+{
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_error("no CUDA device %d", device); return -1.0; }
+    const int sms = device_sm_count(device);
+    const int block = 256, grid = sms * 8, iters = 1 << 15;
+    double* d = nullptr;
+    if (cudaMalloc(&d, (size_t)grid * block * 8) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        fp64_probe_kernel<<<grid, block>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * (double)iters * (double)grid * block;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return best;
+}
+
+}  // extern "C"

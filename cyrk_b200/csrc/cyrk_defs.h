@@ -1,0 +1,121 @@
+// cyrk_defs.h -- constants and plain-old-data shared by host code, device code and
+// NVRTC-compiled user kernels.  Must stay free of host-only includes (NVRTC).
+//
+// Values mirror the reference so that per-trajectory results are interchangeable:
+//   status codes       CyRK/cy/c_common.hpp:25-82
+//   step constants     CyRK/cy/c_common.hpp:189-196   (SAFETY, MIN_FACTOR, MAX_FACTOR, EPS_100)
+//   method ints        CyRK/cy/cysolver.hpp:34-41     (RK23=3, RK45=4, DOP853=5)
+//   brentq tolerances  CyRK/cy/cysolver.hpp:44-46     (4*eps, 4*eps, 100 iterations)
+#pragma once
+
+namespace cyrk {
+
+enum Status : int {
+    ST_CONVERGED = 20,
+    ST_INITIALIZING = 10,
+    ST_EVENT_TERMINATED = 2,
+    ST_SUCCESSFUL_INTEGRATION = 1,
+    ST_NO_ERROR = 0,
+    ST_GENERAL_ERROR = -1,
+    ST_PROPERTY_NOT_SET = -2,
+    ST_UNSUPPORTED_UNKNOWN_MODEL = -3,
+    ST_UNINITIALIZED_CLASS = -4,
+    ST_ATTRIBUTE_ERROR = -7,
+    ST_ARGUMENT_ERROR = -10,
+    ST_DENSE_OUTPUT_NOT_SAVED = -21,
+    ST_BAD_CONFIG_DATA = -22,
+    ST_OPTIMIZE_SIGN_ERROR = -30,
+    ST_OPTIMIZE_CONVERGENCE_ERROR = -31,
+    ST_MEMORY_ALLOCATION_ERROR = -40,
+    ST_MAX_STEPS_USER_EXCEEDED = -52,
+    ST_MAX_STEPS_SYSARCH_EXCEEDED = -53,
+    ST_STEP_SIZE_ERROR_SPACING = -54,
+    ST_STEP_SIZE_ERROR_ACCEPTANCE = -55,
+    ST_INTEGRATION_NOT_SUCCESSFUL = -57,
+    ST_BAD_INITIAL_STEP_SIZE = -80,
+    ST_UNSET_ERROR_CODE = -100
+};
+
+enum Method : int { METHOD_RK23 = 3, METHOD_RK45 = 4, METHOD_DOP853 = 5 };
+
+// Kernel feature variants (compile-time): what one trajectory may produce besides its last row.
+enum Variant : int {
+    VAR_LEAN = 0,   // final row + counters only: no t_eval, no dense store, no events, no row store
+    VAR_ROWS = 1,   // + row store (every accepted step, or the t_eval samples)
+    VAR_FULL = 2,   // + dense-interpolant store + events
+    VAR_COUNT = 3
+};
+
+#define CYRK_MAX_NY 32        // thread-per-trajectory kernels: compile-time n_y up to this
+#define CYRK_MAX_EVENTS 8
+
+// One launch of the thread-per-trajectory solver.  Passed by value (constant bank).
+struct BatchParams {
+    // ---- batch inputs (device pointers)
+    unsigned long long n_traj;
+    const double* y0;            // [n_traj][NY]
+    const char*   args;          // shared blob, or [n_traj][args_stride]
+    unsigned      args_stride;   // bytes; 0 = shared
+    const double* t_span;        // [2] shared, or [n_traj][2]
+    unsigned      t_span_stride; // 0 = shared, 2 = per trajectory
+    double rtol[CYRK_MAX_NY];    // already floored at 100*eps on the host (rk.cpp:600-608)
+    double atol[CYRK_MAX_NY];
+    double max_step;             // INF = none
+    double first_step;           // 0 = automatic
+    unsigned max_num_steps;      // cysolver.cpp:403-410 (RAM cap folded in on the host)
+    int    user_max_steps;       // which of -52 / -53 to report
+    // ---- t_eval (shared by the batch; ascending; for backward runs the host passes the reversed copy)
+    const double* t_eval;
+    unsigned      n_t_eval;
+    // ---- per-trajectory results
+    int*      status;            // [n_traj]
+    unsigned* size;              // rows the reference would have saved
+    unsigned* steps_taken;       // accepted steps
+    unsigned* n_rejected;        // rejected attempts
+    unsigned* nfev;              // RHS evaluations (counted the reference's way)
+    double*   t_last;            // [n_traj]        last saved row
+    double*   y_last;            // [n_traj][NDY]
+    // ---- row store (VAR_ROWS / VAR_FULL): layout follows CySolverResult::solution, row-major by step
+    double*   t_rows;            // [n_traj][row_cap]
+    double*   y_rows;            // [n_traj][row_cap][NDY]
+    unsigned  row_cap;
+    // ---- dense store (VAR_FULL, dense_output): interpolant i covers (dense_t[i-1], dense_t[i]]
+    int       dense_output;
+    double*   dense_t;           // [n_traj][dense_cap]      t_now of interpolant i (entry 0: t_start)
+    double*   dense_state;       // [n_traj][dense_cap][NY*(Q_ORDER+1)]   [y_old | Q], dense.cpp:27-37
+    unsigned* dense_count;       // [n_traj]
+    unsigned  dense_cap;
+    // ---- events (VAR_FULL)
+    int       n_events;
+    int       ev_id[CYRK_MAX_EVENTS];     // index into the problem's event table
+    int       ev_dir[CYRK_MAX_EVENTS];
+    unsigned long long ev_max[CYRK_MAX_EVENTS];   // ~0ull = never terminate
+    double*   ev_t;              // [n_traj][n_events][ev_cap]
+    double*   ev_y;              // [n_traj][n_events][ev_cap][NDY]
+    unsigned* ev_count;          // [n_traj][n_events]
+    int*      ev_term_index;     // [n_traj]   (-1 = none)
+    unsigned  ev_cap;
+    // ---- scheduling
+    unsigned long long* queue;   // global work counter (zeroed before launch)
+    int       refill_min;        // refill a warp when at least this many lanes are idle (1..32)
+};
+
+// Post-hoc dense evaluation (CySolverResult::call_vectorize, cysolution.cpp:511-616).
+struct DenseEvalParams {
+    unsigned long long n_traj;
+    const double* t_query;       // [n_query] shared
+    unsigned      n_query;
+    const double* t_span;        // as above
+    unsigned      t_span_stride;
+    const int*      status;
+    const double*   dense_t;
+    const double*   dense_state;
+    const unsigned* dense_count;
+    unsigned        dense_cap;
+    const char*   args;
+    unsigned      args_stride;
+    double*       out;           // [n_traj][n_query][NDY]
+    int*          code;          // [n_traj]  first non-zero CySolverResult::call status, else 0
+};
+
+}  // namespace cyrk

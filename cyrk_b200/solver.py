@@ -1,0 +1,371 @@
+"""Host-side mirror of the reference call surface for the batched GPU path.
+
+``cysolve_ivp_batch(diffeq, t_span, y0, ...)`` keeps the argument names, defaults and error
+behaviour of ``pysolve_ivp`` / ``cysolve_ivp`` (CyRK/cy/pysolver.pyx:348-403,
+CyRK/cy/cysolver_api.pyx:416-469) but takes a *batch* of initial conditions ``y0[B, n_y]``
+(and optionally per-trajectory ``args[B, n_args]`` / ``t_span[B, 2]``) and runs them in one
+launch through the C ABI (include/cyrk_b200.h).  ``result[i]`` is a view with the attributes of
+the reference's ``WrapCySolverResult`` (cysolver_api.pyx:244-357).
+
+A Python callable cannot run on the GPU, so ``diffeq`` is the *name* of a built-in device functor
+(the reference's benchmark/test problems) or a :class:`UserRHS` compiled from CUDA source.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import CyrkB200Error
+
+INF = float("inf")
+SIZE_MAX = (1 << 64) - 1
+
+# pyhelpers.find_ode_method_int (CyRK/cy/pyhelpers.py:13-23)
+_METHODS = {"rk23": 3, "rk45": 4, "dop853": 5}
+_METHOD_DESCR = {   # CyrkODEMethods, cysolver.hpp:48-66
+    3: "Explicit Runge-Kutta method of order 3(2).",
+    4: "Explicit Runge-Kutta method of order 5(4)",
+    5: "Explicit Runge-Kutta method of order 8. Error is controlled using a combination of 5th and 3rd order interpolators.",
+}
+
+EVENT_IDS = dict(y0_gt_50=0, y1_lt_50=1, t_gt_5=2, lorenz_t_ge_5=3, lorenz_y_range=4, lorenz_args=5,
+                 y0=6, y1=7, t_minus_arg4=8, abs_y0_minus_arg4=9)
+
+STORE_FINAL, STORE_ROWS = 0, 1
+FLAG_STRICT_FP, FLAG_DEVICE_IO = 1, 2
+
+
+def find_ode_method_int(method: str) -> int:
+    m = _METHODS.get(str(method).lower())
+    if m is None:
+        # same exception type/message family as pysolver.pyx:83-87
+        raise NotImplementedError(
+            f"ERROR: `cysolve_ivp_batch` - Unknown or unsupported integration method provided: {method}.\n"
+            f"Supported methods are: RK23, RK45, DOP853.")
+    return m
+
+
+class Event:
+    """Event description: mirrors the attributes the reference reads off event callables
+    (``terminal``, ``max_allowed``, ``direction``; pysolver.pyx:152-200).
+
+    ``func`` is the name of a built-in event functor (see ``EVENT_IDS``) or, for a
+    :class:`UserRHS`, the integer index of an event compiled with it.
+    """
+
+    def __init__(self, func: Union[str, int], direction: int = 0, terminal: bool = False,
+                 max_allowed: Optional[int] = None):
+        self.func = func
+        self.direction = int(direction)
+        if max_allowed is None:
+            max_allowed = 1 if terminal else None
+        self.max_allowed = max_allowed
+        self.terminal = bool(terminal) or (max_allowed is not None)
+
+
+class UserRHS:
+    """A user right-hand side compiled from CUDA C++ with NVRTC (cyrk_b200_rhs_compile).
+
+    The source defines ``__device__ void <entry>(double* dy, double t, const double* y, const char* args)``
+    -- the reference's DiffeqFuncType without the pre-eval pointer (c_common.hpp:218-220) -- and
+    optionally ``__device__ double <entry>_event(int id, double t, const double* y, const char* args)``.
+    """
+
+    def __init__(self, source: str, entry: str, n_y: int, n_extra: int = 0, args_bytes: int = 0, n_events: int = 0):
+        log = C.create_string_buffer(1 << 16)
+        rid = _lib.lib().cyrk_b200_rhs_compile(source.encode(), entry.encode(), n_y, n_extra, args_bytes, n_events,
+                                                log, len(log))
+        self.log = log.value.decode("utf-8", "replace")
+        if rid < 0:
+            raise CyrkB200Error(f"NVRTC compilation failed: {_lib.last_error()}\n{self.log}")
+        self.rhs_id = rid
+        self.n_y, self.n_extra, self.args_bytes, self.n_events = n_y, n_extra, args_bytes, n_events
+
+
+def _rhs_id(diffeq) -> int:
+    if isinstance(diffeq, UserRHS):
+        return diffeq.rhs_id
+    if isinstance(diffeq, (int, np.integer)):
+        return int(diffeq)
+    if isinstance(diffeq, str):
+        rid = _lib.lib().cyrk_b200_rhs_builtin(diffeq.encode())
+        if rid < 0:
+            raise NotImplementedError(f"unknown built-in right-hand side {diffeq!r}")
+        return rid
+    raise TypeError(
+        "diffeq must be the name of a built-in device functor or a UserRHS: a Python callable cannot run on the GPU")
+
+
+def _np_view(ptr, shape, dtype):
+    n = int(np.prod(shape)) if len(shape) else 1
+    if not ptr or n == 0:
+        return np.empty(shape, dtype=dtype)
+    ctype = {np.float64: C.c_double, np.int32: C.c_int32, np.uint32: C.c_uint32}[dtype]
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
+    return arr.reshape(shape)
+
+
+class TrajectoryView:
+    """One trajectory of a :class:`BatchResult` with the WrapCySolverResult attribute surface."""
+
+    def __init__(self, batch: "BatchResult", i: int):
+        self._b, self._i = batch, int(i)
+
+    # --- scalars
+    @property
+    def status(self): return int(self._b.status[self._i])
+    error_code = status
+    @property
+    def success(self): return self.status in (1, 2)
+    @property
+    def message(self): return _lib.status_message(self.status)
+    status_message = message
+    @property
+    def size(self): return int(self._b.size[self._i])
+    @property
+    def steps_taken(self): return int(self._b.steps_taken[self._i])
+    @property
+    def num_y(self): return self._b.num_y
+    @property
+    def num_dy(self): return self._b.num_dy
+    @property
+    def num_events(self): return self._b.num_events
+    @property
+    def integration_method(self): return _METHOD_DESCR[self._b.method]
+    method = integration_method
+
+    # --- arrays (copies, like the reference: cysolver_api.pyx:269-275)
+    @property
+    def t(self):
+        b = self._b
+        if b.t_rows is None:
+            raise CyrkB200Error("rows were not stored: call cysolve_ivp_batch(..., store='rows')")
+        return np.array(b.t_rows[self._i, :self.size])
+
+    @property
+    def y(self):
+        b = self._b
+        if b.y_rows is None:
+            raise CyrkB200Error("rows were not stored: call cysolve_ivp_batch(..., store='rows')")
+        return np.array(b.y_rows[self._i, :self.size, :]).T      # (num_dy, size)
+
+    @property
+    def t_events(self):
+        b = self._b
+        if b.num_events == 0:
+            return None
+        return [np.array(b.event_t[self._i, e, :b.event_count[self._i, e]]) for e in range(b.num_events)]
+
+    @property
+    def y_events(self):
+        b = self._b
+        if b.num_events == 0:
+            return None
+        return [np.array(b.event_y[self._i, e, :b.event_count[self._i, e], :]).T for e in range(b.num_events)]
+
+    @property
+    def event_terminated(self):
+        return self._b.num_events > 0 and int(self._b.event_terminate_index[self._i]) >= 0
+
+    @property
+    def event_terminate_index(self):
+        if self._b.num_events == 0 or int(self._b.event_terminate_index[self._i]) < 0:
+            return SIZE_MAX            # the reference's "size_t nan", cysolution.hpp:53
+        return int(self._b.event_terminate_index[self._i])
+
+    def __call__(self, t):
+        """sol(t): (num_dy, 1) for a scalar, (num_dy, len(t)) for an array (cysolver_api.pyx:96-130)."""
+        ts = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        out, codes = self._b.call(ts)
+        code = int(codes[self._i])
+        if code != 0:
+            raise CyrkB200Error(_lib.status_message(code))
+        return np.array(out[self._i]).T
+
+
+class BatchResult:
+    """Owns the native result handle (device arena + pinned host mirrors) of one batch solve."""
+
+    def __init__(self, handle, method: int, keep_inputs=()):
+        L = _lib.lib()
+        self._h = handle
+        self._keep = keep_inputs
+        self.method = method
+        self.n_traj = B = L.cyrk_b200_get_n_traj(handle)
+        self.num_y = L.cyrk_b200_get_num_y(handle)
+        self.num_dy = ndy = L.cyrk_b200_get_num_dy(handle)
+        self.status = _np_view(L.cyrk_b200_get_status_ptr(handle), (B,), np.int32)
+        self.size = _np_view(L.cyrk_b200_get_size_ptr(handle), (B,), np.uint32)
+        self.steps_taken = _np_view(L.cyrk_b200_get_steps_taken_ptr(handle), (B,), np.uint32)
+        self.n_rejected = _np_view(L.cyrk_b200_get_n_rejected_ptr(handle), (B,), np.uint32)
+        self.nfev = _np_view(L.cyrk_b200_get_nfev_ptr(handle), (B,), np.uint32)
+        self.t_last = _np_view(L.cyrk_b200_get_t_last_ptr(handle), (B,), np.float64)
+        self.y_last = _np_view(L.cyrk_b200_get_y_last_ptr(handle), (B, ndy), np.float64)
+        cap = L.cyrk_b200_get_row_capacity(handle)
+        self.row_capacity = cap
+        self.t_rows = _np_view(L.cyrk_b200_get_t_ptr(handle), (B, cap), np.float64) if cap else None
+        self.y_rows = _np_view(L.cyrk_b200_get_y_ptr(handle), (B, cap, ndy), np.float64) if cap else None
+        self.num_events = ne = L.cyrk_b200_get_num_events(handle)
+        if ne:
+            ec = L.cyrk_b200_get_event_capacity(handle)
+            self.event_count = _np_view(L.cyrk_b200_get_event_count_ptr(handle), (B, ne), np.uint32)
+            self.event_t = _np_view(L.cyrk_b200_get_event_t_ptr(handle), (B, ne, ec), np.float64)
+            self.event_y = _np_view(L.cyrk_b200_get_event_y_ptr(handle), (B, ne, ec, ndy), np.float64)
+            self.event_terminate_index = _np_view(L.cyrk_b200_get_event_terminate_index_ptr(handle), (B,), np.int32)
+        ni = L.cyrk_b200_get_num_interpolates_ptr(handle)
+        self.num_interpolates = _np_view(ni, (B,), np.uint32) if ni else None
+        self.kernel_ms = L.cyrk_b200_get_kernel_ms(handle)
+        self.total_ms = L.cyrk_b200_get_total_ms(handle)
+        self.launches = L.cyrk_b200_get_launch_count(handle)
+        self.h2d_bytes = L.cyrk_b200_get_h2d_bytes(handle)
+        self.d2h_bytes = L.cyrk_b200_get_d2h_bytes(handle)
+
+    @property
+    def success(self):
+        return (self.status == 1) | (self.status == 2)
+
+    def __len__(self):
+        return self.n_traj
+
+    def __getitem__(self, i) -> TrajectoryView:
+        if not -self.n_traj <= i < self.n_traj:
+            raise IndexError(i)
+        return TrajectoryView(self, i % self.n_traj)
+
+    def call(self, t):
+        """Batched sol(t): returns (out[B, len(t), num_dy], codes[B]) -- CySolverResult::call_vectorize
+        for every trajectory in one kernel launch."""
+        ts = np.ascontiguousarray(np.atleast_1d(t), dtype=np.float64)
+        out = np.full((self.n_traj, ts.size, self.num_dy), np.nan)
+        codes = np.zeros(self.n_traj, dtype=np.int32)
+        rc = _lib.lib().cyrk_b200_call_vectorize(self._h, ts.ctypes.data, ts.size, out.ctypes.data, codes.ctypes.data)
+        if rc != 0:
+            raise CyrkB200Error(_lib.last_error())
+        return out, codes
+
+    def close(self):
+        if self._h:
+            _lib.lib().cyrk_b200_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def cysolve_ivp_batch(
+        diffeq,
+        t_span,
+        y0,
+        method: str = "RK45",
+        t_eval=None,
+        dense_output: bool = False,
+        events: Optional[Sequence] = None,
+        args=None,
+        expected_size: int = 0,
+        num_extra: int = 0,
+        first_step: float = 0.0,
+        max_step: float = INF,
+        rtol=1.0e-3,
+        atol=1.0e-6,
+        max_num_steps: int = 0,
+        max_ram_MB: int = 2000,
+        store: str = "rows",
+        strict_fp: bool = False,
+        device: int = 0,
+        solution_reuse: Optional[BatchResult] = None,
+) -> BatchResult:
+    """Solve ``B`` independent initial-value problems on one B200.
+
+    Same names/defaults as ``pysolve_ivp`` (pysolver.pyx:348-368) plus:
+      y0        (B, n_y); args (n_args,) shared or (B, n_args) per trajectory (float64, the
+                reference's ``double[::1] args`` convention) or ``bytes`` for an opaque struct blob;
+                t_span (2,) shared or (B, 2).
+      store     'rows'  -> every row the reference would save (``result[i].t/.y``)
+                'final' -> only the last row and the counters (``result.y_last``)
+      strict_fp run the -fmad=false kernels (the reference's rounding: no FMA contraction)
+    """
+    L = _lib.lib()
+    method_int = find_ode_method_int(method)
+    # pysolver.pyx:255-263
+    if first_step < 0.0:
+        raise AttributeError("ERROR: `cysolve_ivp_batch` - `first_step` must be a positive number (or 0 for automatic).")
+    if max_step <= 0.0:
+        raise AttributeError("ERROR: `cysolve_ivp_batch` - `max_step` must be a postive number.")
+    rid = _rhs_id(diffeq)
+
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    if y0.ndim == 1:
+        y0 = y0[None, :]
+    if y0.ndim != 2:
+        raise ValueError("y0 must have shape (B, n_y)")
+    B, ny = y0.shape
+    ts = np.ascontiguousarray(t_span, dtype=np.float64)
+    if ts.shape not in ((2,), (B, 2)):
+        raise ValueError("t_span must have shape (2,) or (B, 2)")
+    n_t_span = 1 if ts.ndim == 1 else B
+
+    if args is None:
+        a_buf, args_len, n_args = None, 0, 0
+    elif isinstance(args, (bytes, bytearray)):
+        a_buf = np.frombuffer(bytes(args), dtype=np.uint8).copy()
+        args_len, n_args = a_buf.size, 1
+    else:
+        a = np.ascontiguousarray(args, dtype=np.float64)
+        if a.ndim == 1:
+            args_len, n_args = a.size * 8, 1
+        elif a.ndim == 2 and a.shape[0] == B:
+            args_len, n_args = a.shape[1] * 8, B
+        else:
+            raise ValueError("args must have shape (n_args,) or (B, n_args)")
+        a_buf = a
+    rt = np.atleast_1d(np.asarray(rtol, dtype=np.float64)).copy()
+    at = np.atleast_1d(np.asarray(atol, dtype=np.float64)).copy()
+    te = None if t_eval is None else np.ascontiguousarray(t_eval, dtype=np.float64)
+    n_te = 0 if te is None else te.size
+
+    events = list(events) if events else []
+    ev_ids = np.zeros(max(len(events), 1), dtype=np.int32)
+    ev_dirs = np.zeros(max(len(events), 1), dtype=np.int32)
+    ev_max = np.full(max(len(events), 1), SIZE_MAX, dtype=np.uint64)
+    for i, ev in enumerate(events):
+        if not isinstance(ev, Event):
+            ev = Event(*ev) if isinstance(ev, tuple) else Event(ev)
+        ev_ids[i] = EVENT_IDS[ev.func] if isinstance(ev.func, str) else int(ev.func)
+        ev_dirs[i] = ev.direction
+        ev_max[i] = SIZE_MAX if ev.max_allowed is None else int(ev.max_allowed)
+
+    store_mode = {"final": STORE_FINAL, "rows": STORE_ROWS, "steps": STORE_ROWS, "t_eval": STORE_ROWS}[store]
+    flags = FLAG_STRICT_FP if strict_fp else 0
+    call_args = (
+        rid, method_int, B,
+        ts.ctypes.data, n_t_span,
+        y0.ctypes.data, ny,
+        int(num_extra),
+        a_buf.ctypes.data if a_buf is not None else None, args_len, n_args,
+        int(max_num_steps), int(max_ram_MB),
+        int(bool(dense_output)),
+        te.ctypes.data if te is not None else None, n_te,
+        ev_ids.ctypes.data, ev_dirs.ctypes.data, ev_max.ctypes.data, len(events),
+        rt.ctypes.data, rt.size,
+        at.ctypes.data, at.size,
+        float(max_step), float(first_step),
+        int(expected_size),
+        store_mode, flags, int(device))
+    if solution_reuse is not None:
+        # CySolverResult reuse (Documentation/CySolverResult_Reuses.md): same arena, new problem
+        h = solution_reuse._h
+        solution_reuse._h = None
+        if L.cyrk_b200_solve_batch_noreturn(h, *call_args) != 0:
+            L.cyrk_b200_free(h)
+            raise CyrkB200Error(_lib.last_error())
+    else:
+        h = L.cyrk_b200_solve_batch(*call_args)
+        if not h:
+            raise CyrkB200Error(_lib.last_error())
+    return BatchResult(h, method_int)
