@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- trajectory-solves/s of the batched adaptive-RK path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C5|C1|C2|C3] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic initial conditions (the shard of this
+rank).  Default workload = BASELINE.json configs[4] / the north-star target: Lotka-Volterra (n_y=2) RK45,
+rtol=1e-7, atol=1e-9, t_span=(0,10), 8 Mi trajectories PER GPU (weak scaling), store='final'.
+(configs[1] -- 4 Mi Lorenz trajectories x 1000 t_eval samples + dense output -- needs >= 96 GB of samples
+plus ~223 GB of interpolants and does not fit one GPU; it is available at a reduced batch as --workload C2.)
+
+Printed JSON line (rank 0):
+  value     whole-job solves/s, inputs resident in HBM when the timed region starts (CYRK_FLAG_DEVICE_IO),
+            timed on the device with CUDA events on the launching stream, max over ranks
+  e2e       the same metric through the public API with HOST (pinned) buffers: H2D of y0 and D2H of the
+            per-trajectory results are inside the timed region
+  roofline  algorithmic FP64 FLOP/s of the solve kernel (200 FLOP per RK45 attempt for n_y=2,
+            attempts from the kernel's own counters) against the FP64 peak measured in this run by a
+            dependent-free DFMA probe (MEASURED_PEAKS.json has no FP64 figure); the HBM side is reported next
+            to it to show the path is not bandwidth bound
+  cpu_baseline   the reference's own CPU path (oracle/_ref when present, else the C port) on a bounded sample
+
+--impl reference times that CPU path alone (all host threads), same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# F_attempt(m) = n_y*c_m + E_m*F_rhs + s   
+C_M = {"RK23": 25, "RK45": 62, "DOP853": 167}
+E_M = {"RK23": 3, "RK45": 6, "DOP853": 12}
+S_CTRL = {"RK23": 16, "RK45": 22, "DOP853": 34}
+
+WORKLOADS = {
+    # name: rhs, method, n_y, F_rhs, rtol, atol, per-GPU batch, description
+    "C5": dict(rhs="lotkavolterra", method="RK45", ny=2, f_rhs=9, rtol=1e-7, atol=1e-9, batch=8 * 1024 * 1024,
+               descr="C5/C1: Lotka-Volterra (n_y=2) RK45 rtol=1e-7 atol=1e-9 t_span=(0,10), store=final"),
+    "C1": dict(rhs="lotkavolterra", method="RK45", ny=2, f_rhs=9, rtol=1e-7, atol=1e-9, batch=1024 * 1024,
+               descr="C1: Lotka-Volterra (n_y=2) RK45 rtol=1e-7 atol=1e-9 t_span=(0,10), 1 Mi ICs, store=final"),
+    "C2": dict(rhs="lorenz", method="DOP853", ny=3, f_rhs=9, rtol=1e-9, atol=1e-11, batch=256 * 1024,
+               descr="C2 (reduced batch): Lorenz (n_y=3) DOP853 rtol=1e-9 atol=1e-11, rho~U(20,35), store=final"),
+    "C3": dict(rhs="pendulum", method="RK23", ny=2, f_rhs=10, rtol=1e-6, atol=1e-8, batch=1024 * 1024,
+               descr="C3 (no events): pendulum (n_y=2) RK23 rtol=1e-6 atol=1e-8, store=final"),
+}
+
+
+def make_inputs(w, n, seed):
+    """Synthetic inputs of SURVEY.md 8d (numpy default_rng / PCG64)."""
+    rng = np.random.default_rng(seed)
+    if w["rhs"] == "lotkavolterra":
+        y0 = np.stack([rng.uniform(5, 15, n), rng.uniform(2.5, 7.5, n)], 1)
+        args = np.array([1.5, 1.0, 3.0, 1.0])
+    elif w["rhs"] == "lorenz":
+        y0 = np.tile([1.0, 0.0, 0.0], (n, 1))
+        args = np.stack([np.full(n, 10.0), rng.uniform(20, 35, n), np.full(n, 8.0 / 3.0)], 1)
+    else:
+        y0 = np.stack([rng.uniform(-1.5, 1.5, n), rng.uniform(-1, 1, n)], 1)
+        args = np.array([1.0, 1.0, 9.81, 0.0, 0.0])
+    return np.ascontiguousarray(y0), args
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(w, n, threads=None, seed=12345):
+    """The reference's CPU path on `n` trajectories of the workload (prange pattern, all host threads)."""
+    from oracle import oracle as o
+    kind = "reference" if o.have_ref() else "port"
+    impl = "ref" if kind == "reference" else "port"
+    y0, args = make_inputs(w, n, seed)
+    threads = threads or len(os.sched_getaffinity(0))
+    out = o.solve_batch(w["rhs"], (0.0, 10.0), y0, w["method"], w["rtol"], w["atol"], args=args, impl=impl,
+                        n_threads=threads, want_teval=False)
+    ok = bool(np.all(out["status"] == 1))
+    return dict(seconds=out["seconds"], n=n, threads=threads, kind=kind, ok=ok,
+                steps=int(out["steps"].sum()))
+
+
+def run_reference_arm(a, w, rank, world):
+    if rank != 0:
+        return
+    n = 65536
+    for _ in range(a.warmup):
+        cpu_reference_run(w, 4096)
+    secs, kind, threads = 0.0, "port", 1
+    for _ in range(a.steps):
+        r = cpu_reference_run(w, n)
+        secs += r["seconds"]; kind = r["kind"]; threads = r["threads"]
+    value = a.steps * n / secs
+    sample = f"{n} trajectories per step ({a.steps} steps) of the workload's generator, all on rank 0"
+    line = {
+        "impl": "reference", "metric": "trajectory-solves/s", "value": value, "unit": "solves/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["descr"], "trajectories_per_step": n, "host_threads": threads},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C5", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override trajectories per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    w = dict(WORKLOADS[a.workload])
+    if a.batch:
+        w["batch"] = a.batch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if a.impl == "reference":
+        run_reference_arm(a, w, rank, world)
+        return
+
+    import torch
+    import cyrk_b200 as c
+    if not torch.cuda.is_available() or c.lib().cyrk_b200_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = w["batch"]
+    # contiguous shard of the global IC set: rank r owns [r*B, (r+1)*B) -> generated with seed 100 + r
+    y0_h, args_h = make_inputs(w, B, 100 + rank)
+    y0_pin = torch.from_numpy(y0_h).pin_memory()
+    args_pin = torch.from_numpy(np.ascontiguousarray(args_h)).pin_memory()
+    y0_d = y0_pin.to(dev)
+    args_d = args_pin.to(dev)
+    common = dict(method=w["method"], rtol=w["rtol"], atol=w["atol"], store="final", device=local_rank)
+
+    # ---- device-resident arm (value)
+    res = None
+    for _ in range(max(a.warmup, 3)):
+        res = c.cysolve_ivp_batch(w["rhs"], (0.0, 10.0), y0_d, args=args_d, solution_reuse=res, **common)
+    fp64_peak = c.lib().cyrk_b200_measure_fp64_tflops(local_rank)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, ker_ms, launches = 0.0, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        res = c.cysolve_ivp_batch(w["rhs"], (0.0, 10.0), y0_d, args=args_d, solution_reuse=res, **common)
+        dev_ms += res.total_ms           # CUDA events on the shim's launching stream, whole call
+        ker_ms += res.kernel_ms          # CUDA events around the solve kernel only
+        launches += res.launches
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    res.close()
+
+    # ---- end-to-end arm (host pinned buffers through the public API; H2D + D2H inside the timed region)
+    res = None
+    y0_np, args_np = y0_pin.numpy(), args_pin.numpy()
+    for _ in range(2):
+        res = c.cysolve_ivp_batch(w["rhs"], (0.0, 10.0), y0_np, args=args_np, solution_reuse=res, **common)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_dev_ms = 0.0
+    for _ in range(a.steps):
+        res = c.cysolve_ivp_batch(w["rhs"], (0.0, 10.0), y0_np, args=args_np, solution_reuse=res, **common)
+        e2e_dev_ms += res.total_ms
+        _ = float(res.y_last[0, 0])      # touch the result on the host
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    h2d, d2h = res.h2d_bytes, res.d2h_bytes
+    ok = bool((res.status == 1).all())
+    attempts = int(res.steps_taken.sum(dtype=np.int64)) + int(res.n_rejected.sum(dtype=np.int64))
+    steps_acc = int(res.steps_taken.sum(dtype=np.int64))
+    res.close()
+
+    # ---- max over ranks
+    vals = torch.tensor([dev_ms, ker_ms, e2e_wall_ms, wall_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([attempts, steps_acc, launches, int(ok)], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        mn = cnt[3:4].clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        cnt[3] = mn[0]
+    dev_ms, ker_ms, e2e_wall_ms, wall_ms = (float(v) for v in vals.tolist())
+    attempts_all, steps_all, launches_all, ok_all = (int(v) for v in cnt.tolist())
+
+    if rank == 0:
+        total = B * world
+        value = a.steps * total / (dev_ms * 1e-3)
+        e2e_value = a.steps * total / (e2e_wall_ms * 1e-3)
+        f_attempt = w["ny"] * C_M[w["method"]] + E_M[w["method"]] * w["f_rhs"] + S_CTRL[w["method"]]
+        # per-GPU kernel roofline (rank 0's counters; every rank runs the same-size shard)
+        alg_flops_per_launch = attempts * f_attempt
+        ker_ms_per_launch = ker_ms / a.steps
+        achieved_tf = alg_flops_per_launch / (ker_ms_per_launch * 1e-3) / 1e12
+        io_bytes = B * (w["ny"] * 8 + 5 * 4 + 8 + w["ny"] * 8)      # y0 in; counters, t_last, y_last out
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            hbm_peak = 6650.0
+        line = {
+            "metric": "trajectory-solves/s", "value": value, "unit": "solves/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["descr"], "trajectories_per_gpu": B, "t_span": [0.0, 10.0],
+                       "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (io_bytes / 1e6),
+                       "rk_attempts_per_step": attempts_all, "rk_steps_per_s": steps_all * a.steps / (dev_ms * 1e-3) / a.steps,
+                       "all_success": bool(ok_all), "wall_ms_per_step": wall_ms / a.steps},
+            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_wall_ms / a.steps},
+            "gpu_launches": launches_all,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / fp64_peak if fp64_peak and fp64_peak > 0 else None, "traffic": None,
+                         "peak_source": "in-run dependent-free DFMA probe (cyrk_b200_measure_fp64_tflops); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "flop_per_attempt": f_attempt, "kernel_ms_per_launch": ker_ms_per_launch,
+                         "hbm": {"achieved_gbs": io_bytes / (ker_ms_per_launch * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                 "frac": io_bytes / (ker_ms_per_launch * 1e-3) / 1e9 / hbm_peak}},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            # bounded sample: calibrate on 4096 trajectories, then aim for ~10 s of CPU work
+            cal = cpu_reference_run(w, 4096)
+            rate = 4096 / max(cal["seconds"], 1e-6)
+            n = int(min(max(rate * 10.0, 8192), 1 << 21))
+            r = cpu_reference_run(w, n)
+            line["cpu_baseline"] = {"value": r["n"] / r["seconds"], "unit": "solves/s", "cores": r["threads"],
+                                    "kind": r["kind"],
+                                    "sample": f"{r['n']} trajectories of the same generator (seed 12345), "
+                                              f"{r['seconds']:.1f} s on {r['threads']} host threads"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -441,10 +441,10 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const ProblemEntry* 
         CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
 
         // counters come back first: they decide whether any arena overflowed
-        if (download(h, h->h_size, h->d_size, B * 4)) return -1;
+        const bool need_check = want_rows || dense || a.n_events;
+        if ((need_check || !device_io) && download(h, h->h_size, h->d_size, B * 4)) return -1;
         if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
         if (a.n_events && download(h, h->h_ev_count, h->d_ev_count, B * a.n_events * 4)) return -1;
-        bool need_check = want_rows || dense || a.n_events;
         if (!need_check) break;
         CU_TRY(cudaStreamSynchronize(h->stream));
         {

@@ -99,6 +99,23 @@ def _rhs_id(diffeq) -> int:
         "diffeq must be the name of a built-in device functor or a UserRHS: a Python callable cannot run on the GPU")
 
 
+class DeviceArray:
+    """A device-resident result array (CYRK_FLAG_DEVICE_IO).  Implements ``__cuda_array_interface__`` so
+    ``torch.as_tensor(arr, device='cuda')`` / cupy wrap it without a copy.  Valid until the owning
+    BatchResult is closed or re-used."""
+
+    def __init__(self, ptr, shape, dtype, owner):
+        self.ptr, self.shape, self.dtype, self._owner = int(ptr or 0), tuple(int(x) for x in shape), np.dtype(dtype), owner
+
+    @property
+    def __cuda_array_interface__(self):
+        return dict(shape=self.shape, typestr=self.dtype.str, data=(self.ptr, False), version=3, strides=None)
+
+
+def _is_cuda_tensor(x) -> bool:
+    return hasattr(x, "is_cuda") and bool(getattr(x, "is_cuda")) and hasattr(x, "data_ptr")
+
+
 def _np_view(ptr, shape, dtype):
     n = int(np.prod(shape)) if len(shape) else 1
     if not ptr or n == 0:
@@ -189,11 +206,19 @@ class TrajectoryView:
 class BatchResult:
     """Owns the native result handle (device arena + pinned host mirrors) of one batch solve."""
 
-    def __init__(self, handle, method: int, keep_inputs=()):
+    def __init__(self, handle, method: int, keep_inputs=(), device_io: bool = False):
         L = _lib.lib()
         self._h = handle
         self._keep = keep_inputs
         self.method = method
+        self.device_io = device_io
+        if device_io:
+            owner = self
+
+            def _np_view(ptr, shape, dtype):     # noqa: F811 -- device pointers: never dereference on the host
+                return DeviceArray(ptr, shape, dtype, owner)
+        else:
+            _np_view = globals()["_np_view"]
         self.n_traj = B = L.cyrk_b200_get_n_traj(handle)
         self.num_y = L.cyrk_b200_get_num_y(handle)
         self.num_dy = ndy = L.cyrk_b200_get_num_dy(handle)
@@ -238,6 +263,8 @@ class BatchResult:
     def call(self, t):
         """Batched sol(t): returns (out[B, len(t), num_dy], codes[B]) -- CySolverResult::call_vectorize
         for every trajectory in one kernel launch."""
+        if self.device_io:
+            raise CyrkB200Error("call() on a device-resident result: use cyrk_b200_call_vectorize with device pointers")
         ts = np.ascontiguousarray(np.atleast_1d(t), dtype=np.float64)
         out = np.full((self.n_traj, ts.size, self.num_dy), np.nan)
         codes = np.zeros(self.n_traj, dtype=np.int32)
@@ -299,18 +326,52 @@ def cysolve_ivp_batch(
         raise AttributeError("ERROR: `cysolve_ivp_batch` - `max_step` must be a postive number.")
     rid = _rhs_id(diffeq)
 
-    y0 = np.ascontiguousarray(y0, dtype=np.float64)
-    if y0.ndim == 1:
-        y0 = y0[None, :]
-    if y0.ndim != 2:
-        raise ValueError("y0 must have shape (B, n_y)")
-    B, ny = y0.shape
-    ts = np.ascontiguousarray(t_span, dtype=np.float64)
-    if ts.shape not in ((2,), (B, 2)):
-        raise ValueError("t_span must have shape (2,) or (B, 2)")
-    n_t_span = 1 if ts.ndim == 1 else B
+    device_io = _is_cuda_tensor(y0)
+    keep = ()
+    if device_io:
+        # Optional tensor I/O: y0 / args / t_span are contiguous float64 CUDA tensors on `device`;
+        # results stay on the device (BatchResult arrays become DeviceArray objects).
+        import torch
+        y0 = y0.contiguous()
+        if y0.dtype != torch.float64 or y0.dim() != 2:
+            raise ValueError("device y0 must be a float64 CUDA tensor of shape (B, n_y)")
+        B, ny = (int(v) for v in y0.shape)
+        device = y0.device.index if y0.device.index is not None else device
+        ts_t = t_span if _is_cuda_tensor(t_span) else torch.as_tensor(np.asarray(t_span, dtype=np.float64), device=y0.device)
+        ts_t = ts_t.contiguous()
+        n_t_span = 1 if ts_t.dim() == 1 else B
+        a_t = None
+        if args is not None:
+            a_t = args if _is_cuda_tensor(args) else torch.as_tensor(np.asarray(args, dtype=np.float64), device=y0.device)
+            a_t = a_t.contiguous()
+        keep = (y0, ts_t, a_t)
+        torch.cuda.current_stream(y0.device).synchronize()   # inputs were produced on torch's stream
 
-    if args is None:
+        class _P:      # minimal stand-ins exposing .ctypes.data like numpy arrays
+            def __init__(self, t): self.ctypes = type("c", (), {"data": t.data_ptr()})
+        y0 = _P(y0)
+        ts = _P(ts_t)
+        if a_t is None:
+            a_buf, args_len, n_args = None, 0, 0
+        else:
+            a_buf = _P(a_t)
+            args_len = int(a_t.shape[-1]) * 8
+            n_args = 1 if a_t.dim() == 1 else B
+    else:
+        y0 = np.ascontiguousarray(y0, dtype=np.float64)
+        if y0.ndim == 1:
+            y0 = y0[None, :]
+        if y0.ndim != 2:
+            raise ValueError("y0 must have shape (B, n_y)")
+        B, ny = y0.shape
+        ts = np.ascontiguousarray(t_span, dtype=np.float64)
+        if ts.shape not in ((2,), (B, 2)):
+            raise ValueError("t_span must have shape (2,) or (B, 2)")
+        n_t_span = 1 if ts.ndim == 1 else B
+
+    if device_io:
+        pass
+    elif args is None:
         a_buf, args_len, n_args = None, 0, 0
     elif isinstance(args, (bytes, bytearray)):
         a_buf = np.frombuffer(bytes(args), dtype=np.uint8).copy()
@@ -341,7 +402,7 @@ def cysolve_ivp_batch(
         ev_max[i] = SIZE_MAX if ev.max_allowed is None else int(ev.max_allowed)
 
     store_mode = {"final": STORE_FINAL, "rows": STORE_ROWS, "steps": STORE_ROWS, "t_eval": STORE_ROWS}[store]
-    flags = FLAG_STRICT_FP if strict_fp else 0
+    flags = (FLAG_STRICT_FP if strict_fp else 0) | (FLAG_DEVICE_IO if device_io else 0)
     call_args = (
         rid, method_int, B,
         ts.ctypes.data, n_t_span,
@@ -368,4 +429,4 @@ def cysolve_ivp_batch(
         h = L.cyrk_b200_solve_batch(*call_args)
         if not h:
             raise CyrkB200Error(_lib.last_error())
-    return BatchResult(h, method_int)
+    return BatchResult(h, method_int, keep_inputs=keep, device_io=device_io)
