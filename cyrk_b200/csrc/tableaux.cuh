@@ -242,6 +242,76 @@ struct TabDOP853 {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// The same numbers in __constant__ memory.  The constexpr tables above decide AT COMPILE TIME which
+// terms exist; the values themselves are read as constant-bank operands (DFMA R, R, c[0x3][off], R).
+// Without this, sm_100a ptxas materialises every 64-bit literal with two UMOV instructions per use
+// (17 % of all issued instructions in the first profile, profiles/r01_*).
+// ---------------------------------------------------------------------------------------------
+struct StoreRK23 { double c[3]; double a[3][3]; double b[3]; double e[4]; double p[3][4]; };
+struct StoreRK45 { double c[6]; double a[6][6]; double b[6]; double e[7]; double p[4][7]; };
+struct StoreDOP853 { double c[12]; double a[12][12]; double b[12]; double e3[12]; double e5[12];
+                     double cx[3]; double ax[3][15]; double d[4][16]; };
+
+CYRK_HD constexpr StoreRK23 make_store_rk23()
+{
+    StoreRK23 s{};
+    for (int i = 0; i < 3; i++) { s.c[i] = TabRK23::c(i); s.b[i] = TabRK23::b(i); for (int j = 0; j < 3; j++) s.a[i][j] = TabRK23::a(i, j); }
+    for (int j = 0; j < 4; j++) { s.e[j] = TabRK23::e(j); for (int q = 0; q < 3; q++) s.p[q][j] = TabRK23::p(q, j); }
+    return s;
+}
+CYRK_HD constexpr StoreRK45 make_store_rk45()
+{
+    StoreRK45 s{};
+    for (int i = 0; i < 6; i++) { s.c[i] = TabRK45::c(i); s.b[i] = TabRK45::b(i); for (int j = 0; j < 6; j++) s.a[i][j] = TabRK45::a(i, j); }
+    for (int j = 0; j < 7; j++) { s.e[j] = TabRK45::e(j); for (int q = 0; q < 4; q++) s.p[q][j] = TabRK45::p(q, j); }
+    return s;
+}
+CYRK_HD constexpr StoreDOP853 make_store_dop853()
+{
+    StoreDOP853 s{};
+    for (int i = 0; i < 12; i++) {
+        s.c[i] = TabDOP853::c(i); s.b[i] = TabDOP853::b(i); s.e3[i] = TabDOP853::e3(i); s.e5[i] = TabDOP853::e5(i);
+        for (int j = 0; j < 12; j++) s.a[i][j] = TabDOP853::a(i, j);
+    }
+    for (int r = 0; r < 3; r++) { s.cx[r] = TabDOP853::cx(r); for (int j = 0; j < 15; j++) s.ax[r][j] = TabDOP853::ax(r, j); }
+    for (int r = 0; r < 4; r++) for (int j = 0; j < 16; j++) s.d[r][j] = TabDOP853::d(r, j);
+    return s;
+}
+
+static __constant__ StoreRK23 g_store_rk23 = make_store_rk23();
+static __constant__ StoreRK45 g_store_rk45 = make_store_rk45();
+static __constant__ StoreDOP853 g_store_dop853 = make_store_dop853();
+
+template <class Tab> struct TabLd;
+template <> struct TabLd<TabRK23> {
+    __device__ __forceinline__ static double c(int s) { return g_store_rk23.c[s]; }
+    __device__ __forceinline__ static double a(int s, int j) { return g_store_rk23.a[s][j]; }
+    __device__ __forceinline__ static double b(int j) { return g_store_rk23.b[j]; }
+    __device__ __forceinline__ static double e(int j) { return g_store_rk23.e[j]; }
+    __device__ __forceinline__ static double p(int q, int j) { return g_store_rk23.p[q][j]; }
+};
+template <> struct TabLd<TabRK45> {
+    __device__ __forceinline__ static double c(int s) { return g_store_rk45.c[s]; }
+    __device__ __forceinline__ static double a(int s, int j) { return g_store_rk45.a[s][j]; }
+    __device__ __forceinline__ static double b(int j) { return g_store_rk45.b[j]; }
+    __device__ __forceinline__ static double e(int j) { return g_store_rk45.e[j]; }
+    __device__ __forceinline__ static double p(int q, int j) { return g_store_rk45.p[q][j]; }
+};
+template <> struct TabLd<TabDOP853> {
+    __device__ __forceinline__ static double c(int s) { return g_store_dop853.c[s]; }
+    __device__ __forceinline__ static double a(int s, int j) { return g_store_dop853.a[s][j]; }
+    __device__ __forceinline__ static double b(int j) { return g_store_dop853.b[j]; }
+    __device__ __forceinline__ static double e3(int j) { return g_store_dop853.e3[j]; }
+    __device__ __forceinline__ static double e5(int j) { return g_store_dop853.e5[j]; }
+    __device__ __forceinline__ static double cx(int r) { return g_store_dop853.cx[r]; }
+    __device__ __forceinline__ static double ax(int r, int j) { return g_store_dop853.ax[r][j]; }
+    __device__ __forceinline__ static double d(int r, int j) { return g_store_dop853.d[r][j]; }
+    // unused by this method; present so generic code compiles
+    __device__ __forceinline__ static double e(int) { return 0.0; }
+    __device__ __forceinline__ static double p(int, int) { return 0.0; }
+};
+
 template <int METHOD> struct TabFor;
 template <> struct TabFor<METHOD_RK23> { using type = TabRK23; };
 template <> struct TabFor<METHOD_RK45> { using type = TabRK45; };
