@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcyrk_b200.so")
+LIB_PATH = os.environ.get("CYRK_B200_LIB", os.path.join(_HERE, "libcyrk_b200.so"))
 
 c_size_p = C.POINTER(C.c_size_t)
 c_dbl_p = C.POINTER(C.c_double)

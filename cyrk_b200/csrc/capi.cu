@@ -79,7 +79,8 @@ void registry_init()
 // ------------------------------------------------------------------------------------------------
 // options
 // ------------------------------------------------------------------------------------------------
-static int g_opt_refill_min = 8;
+static int g_opt_refill_min = 1;      // with the prep kernel a refill is a few loads: refill immediately
+static int g_opt_prep = 1;            // 1: run rk_prep_kernel first; 0: set trajectories up inside the solve kernel
 static int g_opt_block = 128;
 static int g_opt_ctas_per_sm = 0;
 
@@ -150,7 +151,7 @@ struct Handle {
     DevBuf d_status, d_size, d_steps, d_nrej, d_nfev, d_tlast, d_ylast;
     DevBuf d_trows, d_yrows, d_dense_t, d_dense_state, d_dense_count;
     DevBuf d_ev_t, d_ev_y, d_ev_count, d_ev_term;
-    DevBuf d_q_t, d_q_out, d_q_code, d_scratch;
+    DevBuf d_q_t, d_q_out, d_q_code, d_scratch, d_prep;
     // pinned host mirrors
     PinBuf h_status, h_size, h_steps, h_nrej, h_nfev, h_tlast, h_ylast;
     PinBuf h_trows, h_yrows, h_dense_count, h_ev_t, h_ev_y, h_ev_count, h_ev_term;
@@ -183,7 +184,7 @@ struct Handle {
         if (device >= 0) cudaSetDevice(device);
         DevBuf* dbs[] = {&d_y0, &d_args, &d_tspan, &d_teval, &d_queue, &d_status, &d_size, &d_steps, &d_nrej, &d_nfev,
                          &d_tlast, &d_ylast, &d_trows, &d_yrows, &d_dense_t, &d_dense_state, &d_dense_count, &d_ev_t,
-                         &d_ev_y, &d_ev_count, &d_ev_term, &d_q_t, &d_q_out, &d_q_code, &d_scratch};
+                         &d_ev_y, &d_ev_count, &d_ev_term, &d_q_t, &d_q_out, &d_q_code, &d_scratch, &d_prep};
         for (DevBuf* b : dbs) b->release();
         PinBuf* pbs[] = {&h_status, &h_size, &h_steps, &h_nrej, &h_nfev, &h_tlast, &h_ylast, &h_trows, &h_yrows,
                          &h_dense_count, &h_ev_t, &h_ev_y, &h_ev_count, &h_ev_term, &h_stage};
@@ -435,7 +436,14 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const ProblemEntry* 
             p.ev_cap = (unsigned)ev_cap;
         }
         CU_TRY(cudaMemsetAsync(h->d_queue.p, 0, 8, h->stream));
-        CU_TRY(cudaEventRecord(pass == 0 ? h->ev_k0 : h->ev_k0, h->stream));
+        CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
+        if (g_opt_prep) {
+            if (h->d_prep.ensure(B * (NDY + 2) * 8)) return -1;
+            const int pgrid = (int)std::min<unsigned long long>((B + 255) / 256, (unsigned long long)device_sm_count(h->device) * 16);
+            CU_TRY(pe->prep[a.method - 3](p, h->d_prep.as<double>(), pgrid, 256, h->stream));
+            h->launches++;
+            p.prep = h->d_prep.as<double>();
+        }
         CU_TRY(ke.launch(p, grid, g_opt_block, h->stream));
         h->launches++;
         CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
@@ -809,6 +817,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "refill_min")) { g_opt_refill_min = value; return 0; }
     if (!strcmp(name, "block")) { if (value < 32 || value > 1024 || value % 32) { set_error("block must be a multiple of 32 in [32,1024]"); return -1; } g_opt_block = value; return 0; }
     if (!strcmp(name, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }
+    if (!strcmp(name, "prep")) { g_opt_prep = value ? 1 : 0; return 0; }
     set_error("unknown option '%s'", name);
     return -1;
 }

@@ -96,6 +96,7 @@ struct BatchParams {
     int*      ev_term_index;     // [n_traj]   (-1 = none)
     unsigned  ev_cap;
     // ---- scheduling
+    const double* prep;          // [n_traj][NDY+2] start-up state from rk_prep_kernel, or NULL (set up inline)
     unsigned long long* queue;   // global work counter (zeroed before launch)
     int       refill_min;        // refill a warp when at least this many lanes are idle (1..32)
 };

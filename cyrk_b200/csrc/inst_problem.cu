@@ -33,12 +33,19 @@ cudaError_t dense_eval(const DenseEvalParams& p, int grid, int block, cudaStream
     return cudaGetLastError();
 }
 template <int METHOD>
+cudaError_t prep(const BatchParams& p, double* out, int grid, int block, cudaStream_t s)
+{
+    rk_prep_kernel<CYRK_INST_PROB, METHOD><<<grid, block, 0, s>>>(p, out);
+    return cudaGetLastError();
+}
+template <int METHOD>
 void fill(ProblemEntry* e)
 {
     e->solve[METHOD - 3][VAR_LEAN] = {launch<METHOD, VAR_LEAN>, occupancy<METHOD, VAR_LEAN>, CYRK_STR(CYRK_INST_PROB) "/lean"};
     e->solve[METHOD - 3][VAR_ROWS] = {launch<METHOD, VAR_ROWS>, occupancy<METHOD, VAR_ROWS>, CYRK_STR(CYRK_INST_PROB) "/rows"};
     e->solve[METHOD - 3][VAR_FULL] = {launch<METHOD, VAR_FULL>, occupancy<METHOD, VAR_FULL>, CYRK_STR(CYRK_INST_PROB) "/full"};
     e->dense_eval[METHOD - 3] = dense_eval<METHOD>;
+    e->prep[METHOD - 3] = prep<METHOD>;
 }
 
 }  // namespace

@@ -20,6 +20,7 @@ struct ProblemEntry {
     int ny, nextra, nargs_dbl;
     KernelEntry solve[3][VAR_COUNT];     // [method - 3][variant]
     cudaError_t (*dense_eval[3])(const DenseEvalParams&, int grid, int block, cudaStream_t);
+    cudaError_t (*prep[3])(const BatchParams&, double* prep, int grid, int block, cudaStream_t);
 };
 
 // table[fp_mode][rhs_id]

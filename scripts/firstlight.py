@@ -36,10 +36,11 @@ print("fp64 probe TFLOP/s:", c.lib().cyrk_b200_measure_fp64_tflops(0), flush=Tru
 # rough throughput
 for B in (1 << 20,):
     y0 = np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)
-    for refill in (1, 4, 8, 16, 32):
+    for prep, refill in ((1, 1), (1, 2), (1, 4), (1, 8), (0, 1), (0, 4), (0, 8), (0, 32)):
         c.lib().cyrk_b200_set_option(b"refill_min", refill)
+        c.lib().cyrk_b200_set_option(b"prep", prep)
         for rep in range(2):
             r = c.cysolve_ivp_batch('lotkavolterra', (0, 10), y0, method='RK45', args=[1.5, 1, 3, 1], rtol=1e-7, atol=1e-9, store='final')
         att = int(r.steps_taken.sum()) + int(r.n_rejected.sum())
-        print(f"B={B} refill_min={refill} kernel_ms={r.kernel_ms:.3f} total_ms={r.total_ms:.3f} solves/s={B/r.kernel_ms*1e3:.3e} attempts={att} "
+        print(f"B={B} prep={prep} refill_min={refill} kernel_ms={r.kernel_ms:.3f} total_ms={r.total_ms:.3f} solves/s={B/r.kernel_ms*1e3:.3e} attempts={att} "
               f"alg_TFLOPs={att*200/r.kernel_ms/1e9:.2f} ok={(r.status==1).all()}", flush=True)
