@@ -79,8 +79,11 @@ void registry_init()
 // ------------------------------------------------------------------------------------------------
 // options
 // ------------------------------------------------------------------------------------------------
-static int g_opt_refill_min = 1;      // with the prep kernel a refill is a few loads: refill immediately
-static int g_opt_prep = 1;            // 1: run rk_prep_kernel first; 0: set trajectories up inside the solve kernel
+// Measured on B200 (profiles/r01_notes.md): with the start-up state precomputed by rk_prep_kernel a refill is a
+// handful of loads, so lanes refill immediately (refill_min 1); that wins from ~2 Mi trajectories up (-6 % at
+// 8 Mi).  Below that the extra launch costs more than it saves and inline set-up with refill_min 4 is best.
+static int g_opt_refill_min = 0;      // 0 = automatic (1 with prep, 4 without)
+static int g_opt_prep = -1;           // -1 = automatic (n_traj >= 2 Mi), 1 = always, 0 = never
 static int g_opt_block = 128;
 static int g_opt_ctas_per_sm = 0;
 
@@ -303,7 +306,8 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const ProblemEntry* 
         p.ev_dir[e] = a.event_dirs ? a.event_dirs[e] : 0;
         p.ev_max[e] = a.event_max ? (unsigned long long)a.event_max[e] : ~0ull;
     }
-    p.refill_min = std::min(32, std::max(1, g_opt_refill_min));
+    const bool use_prep = g_opt_prep < 0 ? (B >= (size_t(1) << 21)) : (g_opt_prep != 0);
+    p.refill_min = g_opt_refill_min > 0 ? std::min(32, g_opt_refill_min) : (use_prep ? 1 : 4);
 
     CU_TRY(cudaEventRecord(h->ev_begin, h->stream));
 
@@ -437,7 +441,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const ProblemEntry* 
         }
         CU_TRY(cudaMemsetAsync(h->d_queue.p, 0, 8, h->stream));
         CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
-        if (g_opt_prep) {
+        if (use_prep) {
             if (h->d_prep.ensure(B * (NDY + 2) * 8)) return -1;
             const int pgrid = (int)std::min<unsigned long long>((B + 255) / 256, (unsigned long long)device_sm_count(h->device) * 16);
             CU_TRY(pe->prep[a.method - 3](p, h->d_prep.as<double>(), pgrid, 256, h->stream));
@@ -817,7 +821,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "refill_min")) { g_opt_refill_min = value; return 0; }
     if (!strcmp(name, "block")) { if (value < 32 || value > 1024 || value % 32) { set_error("block must be a multiple of 32 in [32,1024]"); return -1; } g_opt_block = value; return 0; }
     if (!strcmp(name, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }
-    if (!strcmp(name, "prep")) { g_opt_prep = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "prep")) { g_opt_prep = value; return 0; }
     set_error("unknown option '%s'", name);
     return -1;
 }

@@ -196,13 +196,15 @@ def test_results_do_not_depend_on_scheduling():
     B = 20000
     y0 = np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)
     outs = []
-    for refill, block in ((1, 128), (32, 128), (8, 64), (8, 256)):
+    for refill, block, prep in ((1, 128, 0), (32, 128, 0), (8, 64, 1), (8, 256, 0), (1, 128, 1)):
         c.lib().cyrk_b200_set_option(b"refill_min", refill)
         c.lib().cyrk_b200_set_option(b"block", block)
+        c.lib().cyrk_b200_set_option(b"prep", prep)
         r = c.cysolve_ivp_batch("lotkavolterra", (0, 10), y0, method="RK45", args=[1.5, 1, 3, 1], rtol=1e-7, atol=1e-9, store="rows")
         outs.append((np.array(r.status), np.array(r.steps_taken), np.array(r.t_rows), np.array(r.y_rows)))
-    c.lib().cyrk_b200_set_option(b"refill_min", 8)
+    c.lib().cyrk_b200_set_option(b"refill_min", 0)
     c.lib().cyrk_b200_set_option(b"block", 128)
+    c.lib().cyrk_b200_set_option(b"prep", -1)
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
             assert np.array_equal(a, b, equal_nan=True)
