@@ -154,7 +154,7 @@ struct Handle {
     DevBuf d_status, d_size, d_steps, d_nrej, d_nfev, d_tlast, d_ylast;
     DevBuf d_trows, d_yrows, d_dense_t, d_dense_state, d_dense_count;
     DevBuf d_ev_t, d_ev_y, d_ev_count, d_ev_term;
-    DevBuf d_q_t, d_q_out, d_q_code, d_scratch, d_prep;
+    DevBuf d_q_t, d_q_out, d_q_code, d_scratch, d_prep, d_rtol, d_atol;
     // pinned host mirrors
     PinBuf h_status, h_size, h_steps, h_nrej, h_nfev, h_tlast, h_ylast;
     PinBuf h_trows, h_yrows, h_dense_count, h_ev_t, h_ev_y, h_ev_count, h_ev_term;
@@ -187,7 +187,7 @@ struct Handle {
         if (device >= 0) cudaSetDevice(device);
         DevBuf* dbs[] = {&d_y0, &d_args, &d_tspan, &d_teval, &d_queue, &d_status, &d_size, &d_steps, &d_nrej, &d_nfev,
                          &d_tlast, &d_ylast, &d_trows, &d_yrows, &d_dense_t, &d_dense_state, &d_dense_count, &d_ev_t,
-                         &d_ev_y, &d_ev_count, &d_ev_term, &d_q_t, &d_q_out, &d_q_code, &d_scratch, &d_prep};
+                         &d_ev_y, &d_ev_count, &d_ev_term, &d_q_t, &d_q_out, &d_q_code, &d_scratch, &d_prep, &d_rtol, &d_atol};
         for (DevBuf* b : dbs) b->release();
         PinBuf* pbs[] = {&h_status, &h_size, &h_steps, &h_nrej, &h_nfev, &h_tlast, &h_ylast, &h_trows, &h_yrows,
                          &h_dense_count, &h_ev_t, &h_ev_y, &h_ev_count, &h_ev_term, &h_stage};
@@ -506,6 +506,135 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const ProblemEntry* 
     return 0;
 }
 
+// The CTA-per-trajectory path (large n_y; built-ins RHS_LARGEY / RHS_LARGEY_SIMPLE).  Returns 0 / -1.
+static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
+{
+    const size_t B = a.n_traj, N = a.n_y;
+    const bool device_io = (a.flags & CYRK_FLAG_DEVICE_IO) != 0;
+    const bool want_rows = a.store_mode == CYRK_STORE_ROWS;
+    if (a.num_extra != 0) { set_error("the CTA-per-trajectory path does not capture extra outputs yet"); return -1; }
+    if (a.n_events != 0) { set_error("the CTA-per-trajectory path does not support events yet"); return -1; }
+    if (a.dense_output) { set_error("the CTA-per-trajectory path does not store dense output yet (use t_eval)"); return -1; }
+    if (a.n_args == 0 || a.args_len < 8) { set_error("largey problems need args = (decay_rate, ...)"); return -1; }
+    if (N > 0x7fffffffu) { set_error("n_y too large"); return -1; }
+    h->ny = N; h->nx = 0; h->ndy = N; h->q_order = 0;
+    h->n_traj = B; h->n_events = 0; h->n_t_eval = a.n_t_eval;
+    h->dense_output = false; h->device_io = device_io;
+    h->h2d_bytes = h->d2h_bytes = 0; h->launches = 0; h->kernel_ms = 0.f;
+
+    CtaParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_traj = B;
+    p.n = (unsigned)N;
+    p.n_pad = (unsigned)((N + 1) & ~size_t(1));
+    p.max_step = a.max_step;
+    p.first_step = a.first_step;
+    {
+        int uf; size_t mx;
+        find_max_num_steps(N, 0, a.max_num_steps, a.max_ram_MB, &uf, &mx);
+        p.user_max_steps = uf;
+        p.max_num_steps = (unsigned)std::min<size_t>(mx, 0xffffffffu);
+    }
+    CU_TRY(cudaEventRecord(h->ev_begin, h->stream));
+    // tolerances, expanded to n_y entries
+    std::vector<double> rt(N), at(N);
+    for (size_t i = 0; i < N; i++) {
+        double r = a.rtols[a.n_rtols > 1 ? i : 0];
+        if (r < 100.0 * std::numeric_limits<double>::epsilon()) r = 100.0 * std::numeric_limits<double>::epsilon();
+        rt[i] = r;
+        at[i] = a.atols[a.n_atols > 1 ? i : 0];
+    }
+    if (h->d_rtol.ensure(N * 8) || h->d_atol.ensure(N * 8)) return -1;
+    CU_TRY(cudaMemcpyAsync(h->d_rtol.p, rt.data(), N * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->d_atol.p, at.data(), N * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    p.rtol = h->d_rtol.as<double>();
+    p.atol = h->d_atol.as<double>();
+    if (device_io) {
+        p.y0 = a.y0; p.args = a.args; p.t_span = a.t_span;
+    } else {
+        if (upload(h, h->d_y0, a.y0, B * N * 8)) return -1;
+        if (upload(h, h->d_args, a.args, (a.n_args > 1 ? B : 1) * a.args_len)) return -1;
+        if (upload(h, h->d_tspan, a.t_span, a.n_t_span * 16)) return -1;
+        p.y0 = h->d_y0.as<double>(); p.args = h->d_args.as<char>(); p.t_span = h->d_tspan.as<double>();
+    }
+    p.args_stride = a.n_args > 1 ? (unsigned)a.args_len : 0u;
+    p.t_span_stride = a.n_t_span > 1 ? 2u : 0u;
+    h->in_y0 = p.y0; h->in_args = p.args; h->in_tspan = p.t_span; h->tspan_stride = p.t_span_stride; h->args_stride = p.args_stride;
+    std::vector<double> te;
+    if (a.n_t_eval) {
+        te.assign(a.t_eval, a.t_eval + a.n_t_eval);
+        double ts0[2];
+        if (device_io) { CU_TRY(cudaMemcpy(ts0, a.t_span, 16, cudaMemcpyDeviceToHost)); }
+        else { ts0[0] = a.t_span[0]; ts0[1] = a.t_span[1]; }
+        if (!((ts0[1] - ts0[0]) >= 0.0)) std::reverse(te.begin(), te.end());
+        if (h->d_teval.ensure(te.size() * 8)) return -1;
+        CU_TRY(cudaMemcpyAsync(h->d_teval.p, te.data(), te.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        p.t_eval = h->d_teval.as<double>();
+        p.n_t_eval = (unsigned)a.n_t_eval;
+    }
+    if (h->d_status.ensure(B * 4) || h->d_size.ensure(B * 4) || h->d_steps.ensure(B * 4) || h->d_nrej.ensure(B * 4) ||
+        h->d_nfev.ensure(B * 4) || h->d_tlast.ensure(B * 8) || h->d_ylast.ensure(B * N * 8) || h->d_queue.ensure(8))
+        return -1;
+    p.status = h->d_status.as<int>(); p.size = h->d_size.as<unsigned>(); p.steps_taken = h->d_steps.as<unsigned>();
+    p.n_rejected = h->d_nrej.as<unsigned>(); p.nfev = h->d_nfev.as<unsigned>();
+    p.t_last = h->d_tlast.as<double>(); p.y_last = h->d_ylast.as<double>();
+    p.queue = h->d_queue.as<unsigned long long>();
+
+    // launch geometry: one CTA per SM when the working set fills shared memory, more when it is small
+    int optin = 0;
+    CU_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    const int nvec = cta_num_vectors(a.method);
+    const size_t vec_bytes = (size_t)p.n_pad * 8;
+    size_t fit = ((size_t)optin - 1024) / vec_bytes;
+    p.n_smem_vec = (unsigned)std::min<size_t>(fit, (size_t)nvec);
+    const size_t smem = (size_t)p.n_smem_vec * vec_bytes;
+    const int block = N <= 256 ? 128 : N <= 1024 ? 256 : N <= 2048 ? 512 : 1024;
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)(2048 / block), ((size_t)optin) / (smem + 2048)}));
+    int grid = (int)std::min<unsigned long long>((unsigned long long)device_sm_count(h->device) * per_sm, B);
+    const size_t n_glob = (size_t)nvec - p.n_smem_vec;
+    if (h->d_scratch.ensure((size_t)grid * (n_glob + 2) * vec_bytes)) return -1;
+    p.scratch = h->d_scratch.as<double>();
+
+    size_t row_cap = 0;
+    if (want_rows) row_cap = a.n_t_eval ? a.n_t_eval : (a.expected_size ? a.expected_size : 64);
+    for (int pass = 0; pass < 2; pass++) {
+        if (want_rows) {
+            if (h->d_trows.ensure(B * row_cap * 8) || h->d_yrows.ensure(B * row_cap * N * 8)) return -1;
+            p.t_rows = h->d_trows.as<double>(); p.y_rows = h->d_yrows.as<double>(); p.row_cap = (unsigned)row_cap;
+        }
+        CU_TRY(cudaMemsetAsync(h->d_queue.p, 0, 8, h->stream));
+        CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
+        CU_TRY((fp == FP_STRICT ? cta_launch_strict : cta_launch_fast)(a.rhs_id, a.method, p, grid, block, smem, h->stream));
+        h->launches++;
+        CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
+        if ((want_rows || !device_io) && download(h, h->h_size, h->d_size, B * 4)) return -1;
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; }
+        if (!want_rows) break;
+        size_t mx = 0;
+        const unsigned* sz = h->h_size.as<unsigned>();
+        for (size_t i = 0; i < B; i++) mx = std::max<size_t>(mx, sz[i]);
+        if (mx <= row_cap) break;
+        if (pass == 1) { set_error("internal: arena overflow after the exact-capacity re-run"); return -1; }
+        row_cap = mx;
+    }
+    h->row_cap = row_cap; h->dense_cap = 0; h->ev_cap = 0;
+    if (!device_io) {
+        if (download(h, h->h_status, h->d_status, B * 4) || download(h, h->h_steps, h->d_steps, B * 4) ||
+            download(h, h->h_nrej, h->d_nrej, B * 4) || download(h, h->h_nfev, h->d_nfev, B * 4) ||
+            download(h, h->h_tlast, h->d_tlast, B * 8) || download(h, h->h_ylast, h->d_ylast, B * N * 8))
+            return -1;
+        if (want_rows && (download(h, h->h_trows, h->d_trows, B * row_cap * 8) || download(h, h->h_yrows, h->d_yrows, B * row_cap * N * 8)))
+            return -1;
+    }
+    CU_TRY(cudaEventRecord(h->ev_end, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&h->total_ms, h->ev_begin, h->ev_end);
+    return 0;
+}
+
 static int validate(const SolveArgs& a)
 {
     if (a.n_traj == 0) { set_error("n_traj must be > 0"); return -1; }
@@ -547,8 +676,9 @@ static int solve_impl(Handle* h, const SolveArgs& a)
     h->rhs_id = a.rhs_id; h->method = a.method; h->fp_mode = fp;
 
     if (a.rhs_id == CYRK_RHS_LARGEY || a.rhs_id == CYRK_RHS_LARGEY_SIMPLE) {
-        set_error("CTA-per-trajectory path not built yet");
-        return -1;
+        if (solve_cta_path(h, a, fp)) return -1;
+        h->solved = true;
+        return 0;
     }
     if (a.rhs_id >= CYRK_RHS_USER_BASE) {
         set_error("NVRTC user right-hand sides not built yet");

@@ -1,0 +1,49 @@
+// inst_cta.cu -- instantiates the CTA-per-trajectory kernels (both large built-in problems, three methods) for
+// ONE floating-point mode: compiled twice by the Makefile (-DCYRK_FP_NS=fast -fmad=true / strict -fmad=false).
+#include "cta_core.cuh"
+#include "problems_large.cuh"
+#include "problems_builtin.cuh"
+#include "cta_solver.h"
+
+#define CYRK_CAT2_(a, b) a##b
+#define CYRK_CAT2(a, b) CYRK_CAT2_(a, b)
+
+namespace cyrk {
+namespace CYRK_FP_NS {
+namespace {
+template <class Prob, int METHOD>
+cudaError_t go(const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(rk_cta_kernel<Prob, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rk_cta_kernel<Prob, METHOD><<<grid, block, smem, s>>>(p);
+    return cudaGetLastError();
+}
+template <class Prob>
+cudaError_t by_method(int method, const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
+{
+    switch (method) {
+    case METHOD_RK23: return go<Prob, METHOD_RK23>(p, grid, block, smem, s);
+    case METHOD_RK45: return go<Prob, METHOD_RK45>(p, grid, block, smem, s);
+    case METHOD_DOP853: return go<Prob, METHOD_DOP853>(p, grid, block, smem, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+}  // namespace
+}  // namespace CYRK_FP_NS
+
+cudaError_t CYRK_CAT2(cta_launch_, CYRK_FP_NS)(int rhs_id, int method, const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
+{
+    if (rhs_id == RHS_LARGEY) return CYRK_FP_NS::by_method<ProbLargeY>(method, p, grid, block, smem, s);
+    if (rhs_id == RHS_LARGEY_SIMPLE) return CYRK_FP_NS::by_method<ProbLargeYSimple>(method, p, grid, block, smem, s);
+    return cudaErrorInvalidValue;
+}
+
+#if !CYRK_FP_STRICT
+int cta_num_vectors(int method)
+{
+    return method == METHOD_RK23 ? 2 + TabRK23::NK_DENSE : method == METHOD_RK45 ? 2 + TabRK45::NK_DENSE : 2 + TabDOP853::NK_DENSE;
+}
+#endif
+
+}  // namespace cyrk

@@ -1,0 +1,37 @@
+// problems_large.cuh -- built-in LARGE systems for the CTA-per-trajectory path, as component-wise functors:
+//     eval(i, t, y[n], n, args, aux) -> dy_i        prepare(args, n, aux, reuse)  (cooperative, once per trajectory)
+// Restated from CyRK/cy/cysolver_test.pyx:224-244 / Performance/largey.py:8-44, with n taken from the batch
+// (the reference hard-codes 10 000) and args = (decay_rate[, n]).
+#pragma once
+
+namespace cyrk {
+
+struct ProbLargeY {
+    // r_i = r * 0.9999^(i+1) by SEQUENTIAL multiplication like the reference loop (one thread; shared args are
+    // prepared once per CTA), so the rates are bit-identical to the reference's.
+    __device__ __forceinline__ static void prepare(const char* args, unsigned n, double* aux, bool reuse)
+    {
+        if (!reuse && threadIdx.x == 0) {
+            double r = reinterpret_cast<const double*>(args)[0];
+            for (unsigned i = 0; i < n; i++) { r *= 0.9999; aux[i] = r; }
+        }
+        __syncthreads();
+    }
+    __device__ __forceinline__ static double eval(unsigned i, double t, const double* y, unsigned n, const char*, const double* aux)
+    {
+        const double pi = 3.14159265358979323846;
+        if (i < (n - 1)) return aux[i] * y[i] * sin(2 * pi * t / 5.0 + y[i + 1] / 50.0);
+        return aux[i] * y[i] * sin(2 * pi * t / 5.0);
+    }
+};
+
+struct ProbLargeYSimple {
+    __device__ __forceinline__ static void prepare(const char*, unsigned, double*, bool) { __syncthreads(); }
+    __device__ __forceinline__ static double eval(unsigned i, double t, const double*, unsigned, const char*, const double*)
+    {
+        const double pi = 3.14159265358979323846;
+        return i == 0 ? sin(2.0 * pi * t / 10.0) : 0.0;
+    }
+};
+
+}  // namespace cyrk

@@ -1,0 +1,76 @@
+"""GPU: the CTA-per-trajectory path (large n_y) against the oracle and the golden vectors."""
+import numpy as np
+import pytest
+
+import cyrk_b200 as c
+from cases import cases
+
+pytestmark = pytest.mark.gpu
+CASES = cases()
+
+
+def _tol(ref, rtol, atol):
+    return 10 * rtol * np.abs(ref) + 10 * atol
+
+
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fma"])
+@pytest.mark.parametrize("name", ["largey_rk45_n96", "largey_simple_rk45_n64"])
+def test_golden_large(golden, name, strict):
+    kw = dict(CASES[name])
+    rhs = kw.pop("rhs"); y0 = np.asarray(kw.pop("y0"))[None, :]; ts = kw.pop("t_span")
+    r = c.cysolve_ivp_batch(rhs, ts, y0, strict_fp=strict, **kw)
+    sc = golden[f"{name}/scalars"]
+    v = r[0]
+    assert (v.status, v.size, v.steps_taken) == (sc[0], sc[1], sc[2])
+    assert int(r.nfev[0]) == sc[4]
+    assert np.allclose(v.t, golden[f"{name}/t"], rtol=1e-6, atol=1e-12)
+    yr = golden[f"{name}/y"]
+    assert np.all(np.abs(v.y - yr) <= _tol(yr, kw["rtol"], kw["atol"]))
+
+
+@pytest.mark.parametrize("method", ["RK23", "RK45", "DOP853"])
+@pytest.mark.parametrize("n", [37, 300])
+def test_large_methods_and_t_eval(oracle, method, n):
+    rng = np.random.default_rng(5)
+    B = 6
+    y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (B, n)))
+    args = np.stack([rng.uniform(-0.6, -0.4, B), np.full(B, float(n))], 1)       # per-trajectory decay rate
+    te = np.linspace(0, 10, 9)
+    for t_eval in (None, te):
+        r = c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method=method, args=args, rtol=1e-6, atol=1e-8, t_eval=t_eval)
+        for i in range(B):
+            ref = oracle.solve("largey", (0.0, 10.0), y0[i], method, 1e-6, 1e-8, args=args[i], t_eval=t_eval)
+            v = r[i]
+            assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken), (method, n, i)
+            assert int(r.nfev[i]) == ref.nfev
+            assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)      # parity metric: accepted-t sequence within 1e-6 relative
+            assert np.all(np.abs(v.y - ref.y) <= _tol(ref.y, 1e-6, 1e-8))
+            assert np.all(np.abs(r.y_last[i] - ref.y[:, -1]) <= _tol(ref.y[:, -1], 1e-6, 1e-8))
+
+
+def test_c4_largey_4096(oracle):
+    """BASELINE config 4 shape (n_y = 4096, RK45, rtol 1e-6 / atol 1e-8) on a few trajectories vs the oracle."""
+    rng = np.random.default_rng(3)
+    B, n = 6, 4096
+    y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (B, n)))
+    r = c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method="RK45", args=[-0.5, float(n)], rtol=1e-6, atol=1e-8)
+    ob = oracle.solve_batch("largey", (0.0, 10.0), y0, "RK45", 1e-6, 1e-8, args=[-0.5, float(n)], impl="port")
+    assert np.array_equal(r.status, ob["status"]) and (r.status == 1).all()
+    assert np.array_equal(r.steps_taken, ob["steps"]) and np.array_equal(r.size, ob["size"])
+    assert np.all(np.abs(r.y_last - ob["y_last"]) <= _tol(ob["y_last"], 1e-6, 1e-8))
+    # rows are complete and time-ordered
+    for i in range(B):
+        assert np.all(np.diff(r[i].t) > 0) and r[i].t[-1] == 10.0 and r[i].y.shape == (n, r[i].size)
+
+
+def test_largey_simple_and_unsupported_features():
+    n = 2048
+    y0 = 100.0 * np.ones((3, n))
+    r = c.cysolve_ivp_batch("largey_simple", (0.0, 10.0), y0, method="RK45", args=[-0.5, float(n)], rtol=1e-6, atol=1e-8, store="final")
+    assert (r.status == 1).all()
+    # dy_0 = sin(2 pi t / 10), the rest is constant: y_0(10) = 100 + (10/2pi)(1 - cos(2 pi)) = 100
+    assert np.allclose(r.y_last[:, 0], 100.0, atol=5e-3) and np.all(r.y_last[:, 1:] == 100.0)
+    with pytest.raises(c.CyrkB200Error):
+        c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, args=[-0.5, float(n)], dense_output=True)
+    with pytest.raises(c.CyrkB200Error):
+        c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, args=[-0.5, float(n)], events=[c.Event("y0")])
