@@ -29,7 +29,7 @@ namespace cyrk {
 // ------------------------------------------------------------------------------------------------
 // error reporting
 // ------------------------------------------------------------------------------------------------
-static thread_local std::string g_last_error;
+thread_local std::string g_last_error;
 
 void set_error(const char* fmt, ...)
 {
@@ -204,6 +204,51 @@ struct Handle {
     ~Handle() { destroy_cuda(); }
 };
 
+// Built-in (precompiled) or user (NVRTC) kernels behind one interface.
+struct Dispatch {
+    int rhs_id = -1;
+    bool strict = false;
+    int device = 0;
+    const ProblemEntry* pe = nullptr;       // null => user right-hand side
+    int ny = 0, nextra = 0, nargs_dbl = 0;
+    const char* name(int method, int variant) const { return pe ? pe->solve[method - 3][variant].name : "user"; }
+    cudaError_t occupancy(int method, int variant, int* ctas, int block) const
+    {
+        if (pe) return pe->solve[method - 3][variant].occupancy(ctas, block);
+        return user_rhs_occupancy(rhs_id, method, variant, strict, device, ctas, block);
+    }
+    cudaError_t launch(int method, int variant, const BatchParams& p, int grid, int block, cudaStream_t s) const
+    {
+        if (pe) return pe->solve[method - 3][variant].launch(p, grid, block, s);
+        return user_rhs_launch_solve(rhs_id, method, variant, strict, device, p, grid, block, s);
+    }
+    cudaError_t prep(int method, const BatchParams& p, double* out, int grid, int block, cudaStream_t s) const
+    {
+        if (pe) return pe->prep[method - 3](p, out, grid, block, s);
+        return user_rhs_launch_prep(rhs_id, method, strict, device, p, out, grid, block, s);
+    }
+    cudaError_t dense(int method, const DenseEvalParams& p, int grid, int block, cudaStream_t s) const
+    {
+        if (pe) return pe->dense_eval[method - 3](p, grid, block, s);
+        return user_rhs_launch_dense(rhs_id, method, strict, device, p, grid, block, s);
+    }
+};
+
+static bool make_dispatch(int rhs_id, int fp, int device, Dispatch* d)
+{
+    d->rhs_id = rhs_id; d->strict = fp == FP_STRICT; d->device = device;
+    if (rhs_id >= CYRK_RHS_USER_BASE) {
+        int ne = 0;
+        if (user_rhs_info(rhs_id, &d->ny, &d->nextra, &d->nargs_dbl, &ne)) return false;
+        d->pe = nullptr;
+        return true;
+    }
+    d->pe = registry_lookup(fp, rhs_id);
+    if (!d->pe) return false;
+    d->ny = d->pe->ny; d->nextra = d->pe->nextra; d->nargs_dbl = d->pe->nargs_dbl;
+    return true;
+}
+
 // cy/c_common.cpp:20-56
 static void find_max_num_steps(size_t ny, size_t nx, size_t user, size_t ram_MB, int* user_flag, size_t* out)
 {
@@ -267,14 +312,13 @@ static int device_sm_count(int dev)
 }
 
 // The thread-per-trajectory path.  Returns 0 / -1.
-static int solve_thread_path(Handle* h, const SolveArgs& a, const ProblemEntry* pe)
+static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
 {
     const size_t B = a.n_traj, NY = pe->ny, NX = pe->nextra, NDY = NY + NX;
     const bool device_io = (a.flags & CYRK_FLAG_DEVICE_IO) != 0;
     const bool want_rows = a.store_mode == CYRK_STORE_ROWS;
     const bool dense = a.dense_output != 0;
     const int variant = (dense || a.n_events > 0) ? VAR_FULL : ((want_rows || a.n_t_eval > 0) ? VAR_ROWS : VAR_LEAN);
-    const KernelEntry& ke = pe->solve[a.method - 3][variant];
     const int q_order = a.method == CYRK_METHOD_RK23 ? 3 : a.method == CYRK_METHOD_RK45 ? 4 : 7;
 
     h->ny = NY; h->nx = NX; h->ndy = NDY; h->q_order = q_order;
@@ -405,8 +449,12 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const ProblemEntry* 
     {
         int ctas = g_opt_ctas_per_sm;
         if (ctas <= 0) {
-            CU_TRY(ke.occupancy(&ctas, g_opt_block));
-            if (ctas <= 0) { set_error("kernel %s cannot be resident with %d threads per CTA", ke.name, g_opt_block); return -1; }
+            if (pe->occupancy(a.method, variant, &ctas, g_opt_block) != cudaSuccess) {
+                if (g_last_error.empty()) set_error("occupancy query failed for %s", pe->name(a.method, variant));
+                cudaGetLastError();
+                return -1;
+            }
+            if (ctas <= 0) { set_error("kernel %s cannot be resident with %d threads per CTA", pe->name(a.method, variant), g_opt_block); return -1; }
         }
         grid = device_sm_count(h->device) * ctas;
         const unsigned long long need = (B + g_opt_block - 1) / g_opt_block;
@@ -444,11 +492,11 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const ProblemEntry* 
         if (use_prep) {
             if (h->d_prep.ensure(B * (NDY + 2) * 8)) return -1;
             const int pgrid = (int)std::min<unsigned long long>((B + 255) / 256, (unsigned long long)device_sm_count(h->device) * 16);
-            CU_TRY(pe->prep[a.method - 3](p, h->d_prep.as<double>(), pgrid, 256, h->stream));
+            if (pe->prep(a.method, p, h->d_prep.as<double>(), pgrid, 256, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("prep kernel launch failed"); return -1; }
             h->launches++;
             p.prep = h->d_prep.as<double>();
         }
-        CU_TRY(ke.launch(p, grid, g_opt_block, h->stream));
+        if (pe->launch(a.method, variant, p, grid, g_opt_block, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("solve kernel launch failed"); return -1; }
         h->launches++;
         CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
 
@@ -680,12 +728,10 @@ static int solve_impl(Handle* h, const SolveArgs& a)
         h->solved = true;
         return 0;
     }
-    if (a.rhs_id >= CYRK_RHS_USER_BASE) {
-        set_error("NVRTC user right-hand sides not built yet");
-        return -1;
-    }
-    const ProblemEntry* pe = registry_lookup(fp, a.rhs_id);
-    if (!pe) { set_error("unknown right-hand side id %d", a.rhs_id); return -1; }
+    Dispatch disp;
+    g_last_error.clear();
+    if (!make_dispatch(a.rhs_id, fp, a.device, &disp)) { set_error("unknown right-hand side id %d", a.rhs_id); return -1; }
+    const Dispatch* pe = &disp;
     if ((size_t)pe->ny != a.n_y) { set_error("right-hand side %d has n_y = %d but y0 has n_y = %zu", a.rhs_id, pe->ny, a.n_y); return -1; }
     if ((size_t)pe->nextra != a.num_extra) {
         set_error("right-hand side %d produces %d extra outputs but num_extra = %zu", a.rhs_id, pe->nextra, a.num_extra);
@@ -696,7 +742,7 @@ static int solve_impl(Handle* h, const SolveArgs& a)
         return -1;
     }
     for (size_t e = 0; e < a.n_events; e++)
-        if (a.event_ids[e] < 0 || a.event_ids[e] >= EV_TABLE_SIZE) { set_error("unknown event id %d", a.event_ids[e]); return -1; }
+        if (a.event_ids[e] < 0 || (a.rhs_id < CYRK_RHS_USER_BASE && a.event_ids[e] >= EV_TABLE_SIZE)) { set_error("unknown event id %d", a.event_ids[e]); return -1; }
     if (solve_thread_path(h, a, pe)) return -1;
     h->solved = true;
     return 0;
@@ -803,6 +849,14 @@ int cyrk_b200_rhs_info(int rhs_id, size_t* n_y, size_t* n_extra, size_t* args_by
         if (args_bytes) *args_bytes = 16;
         return 0;
     }
+    if (rhs_id >= CYRK_RHS_USER_BASE) {
+        int a = 0, b = 0, c = 0, d = 0;
+        if (user_rhs_info(rhs_id, &a, &b, &c, &d)) { set_error("unknown right-hand side id %d", rhs_id); return -1; }
+        if (n_y) *n_y = (size_t)a;
+        if (n_extra) *n_extra = (size_t)b;
+        if (args_bytes) *args_bytes = (size_t)c * 8;
+        return 0;
+    }
     const ProblemEntry* pe = registry_lookup(FP_FAST, rhs_id);
     if (!pe) { set_error("unknown right-hand side id %d", rhs_id); return -1; }
     if (n_y) *n_y = pe->ny;
@@ -811,11 +865,10 @@ int cyrk_b200_rhs_info(int rhs_id, size_t* n_y, size_t* n_extra, size_t* args_by
     return 0;
 }
 
-int cyrk_b200_rhs_compile(const char*, const char*, size_t, size_t, size_t, size_t, char* log, size_t log_len)
+int cyrk_b200_rhs_compile(const char* source, const char* entry, size_t n_y, size_t n_extra, size_t args_bytes,
+                          size_t n_event_funcs, char* log, size_t log_len)
 {
-    if (log && log_len) snprintf(log, log_len, "NVRTC path not built yet");
-    set_error("NVRTC path not built yet");
-    return -1;
+    return user_rhs_register(source, entry, n_y, n_extra, args_bytes, n_event_funcs, log, log_len);
 }
 
 void* cyrk_b200_result_create(void) { return new Handle(); }
@@ -899,8 +952,8 @@ int cyrk_b200_call_vectorize(void* hv, const double* t, size_t n_t, double* out,
         else memcpy(codes, st.data(), B * 4);
         return 0;
     }
-    const ProblemEntry* pe = registry_lookup(h->fp_mode, h->rhs_id);
-    if (!pe) { set_error("dense evaluation is not available for right-hand side %d", h->rhs_id); return -1; }
+    Dispatch disp;
+    if (!make_dispatch(h->rhs_id, h->fp_mode, h->device, &disp)) { set_error("dense evaluation is not available for right-hand side %d", h->rhs_id); return -1; }
     DenseEvalParams q;
     memset(&q, 0, sizeof(q));
     q.n_traj = B;
@@ -930,7 +983,7 @@ int cyrk_b200_call_vectorize(void* hv, const double* t, size_t n_t, double* out,
     const int block = 256;
     const unsigned long long grid = (total + block - 1) / block;
     if (grid > 0x7fffffffull) { set_error("too many query points"); return -1; }
-    CU_TRY(pe->dense_eval[h->method - 3](q, (int)grid, block, h->stream));
+    if (disp.dense(h->method, q, (int)grid, block, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("dense evaluation launch failed"); return -1; }
     if (!h->device_io) {
         CU_TRY(cudaMemcpyAsync(out, d_out, B * n_t * NDY * 8, cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaMemcpyAsync(codes, q.code, B * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -1,0 +1,91 @@
+"""User right-hand sides compiled with NVRTC behind the same C ABI (cyrk_b200_rhs_compile)."""
+import numpy as np
+import pytest
+
+import cyrk_b200 as c
+
+LV_SRC = r'''
+// same signature family as the reference's DiffeqFuncType (c_common.hpp:218-220)
+__device__ void my_lv(double* dy, double t, const double* y, const char* args) {
+    const double* p = (const double*)args;
+    const double a = p[0], b = p[1], cc = p[2], d = p[3];
+    const double y0 = y[0], y1 = y[1];
+    dy[0] = a * y0 - b * y0 * y1;
+    dy[1] = -cc * y1 + d * y0 * y1;
+}
+'''
+
+DRAG_SRC = r'''
+struct PendArgs { double l, m, g, c, stop; };          // opaque struct blob, Advanced_CySolver.md:7-13
+__device__ double torque_of(double t) { return 0.1 * sin(t); }     // a "pre-eval" helper is just another function
+__device__ void drag(double* dy, double t, const double* y, const char* args) {
+    const PendArgs* p = (const PendArgs*)args;
+    const double coeff_1 = (-3. * p->g / (2. * p->l));
+    const double coeff_2 = (3. / (p->m * (p->l * p->l)));
+    const double torque = torque_of(t);
+    dy[0] = y[1];
+    double d1 = coeff_1 * sin(y[0]) + coeff_2 * torque;
+    d1 -= p->c * y[1];
+    dy[1] = d1;
+    dy[2] = torque;
+}
+__device__ double drag_event(int id, double t, const double* y, const char* args) {
+    const PendArgs* p = (const PendArgs*)args;
+    if (id == 0) return y[0];
+    if (id == 1) return y[1];
+    return t - p->stop;
+}
+'''
+
+
+def test_compile_cache_and_error_log():
+    u = c.UserRHS(LV_SRC, "my_lv", n_y=2, args_bytes=32)
+    assert u.rhs_id >= 1000
+    assert c.UserRHS(LV_SRC, "my_lv", n_y=2, args_bytes=32).rhs_id == u.rhs_id      # cached by source hash
+    import ctypes as C
+    a, b, d = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    assert c.lib().cyrk_b200_rhs_info(u.rhs_id, C.byref(a), C.byref(b), C.byref(d)) == 0
+    assert (a.value, b.value, d.value) == (2, 0, 32)
+    with pytest.raises(c.CyrkB200Error, match="undefined"):
+        c.UserRHS("__device__ void bad(double* dy, double t, const double* y, const char* a) { dy[0] = nope; }", "bad", n_y=1)
+    with pytest.raises(c.CyrkB200Error):
+        c.UserRHS(LV_SRC, "my_lv", n_y=64)
+
+
+@pytest.mark.gpu
+def test_user_lv_equals_builtin():
+    u = c.UserRHS(LV_SRC, "my_lv", n_y=2, args_bytes=32)
+    rng = np.random.default_rng(0)
+    B = 4096
+    y0 = np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)
+    for method in ("RK23", "RK45", "DOP853"):
+        kw = dict(method=method, args=[1.5, 1, 3, 1], rtol=1e-6, atol=1e-8)
+        a = c.cysolve_ivp_batch(u, (0, 10), y0, strict_fp=True, **kw)
+        b = c.cysolve_ivp_batch("lotkavolterra", (0, 10), y0, strict_fp=True, **kw)
+        assert np.array_equal(a.status, b.status) and np.array_equal(a.steps_taken, b.steps_taken)
+        assert np.array_equal(a.y_last, b.y_last)                  # -fmad=false: NVRTC and nvcc agree bit for bit
+        a = c.cysolve_ivp_batch(u, (0, 10), y0, **kw)
+        b = c.cysolve_ivp_batch("lotkavolterra", (0, 10), y0, **kw)
+        assert np.array_equal(a.status, b.status) and (a.steps_taken == b.steps_taken).mean() >= 0.999
+        assert np.all(np.abs(a.y_last - b.y_last) <= 10 * 1e-6 * np.abs(b.y_last) + 10 * 1e-8)
+
+
+@pytest.mark.gpu
+def test_user_rhs_with_struct_args_events_extras_dense(oracle):
+    u = c.UserRHS(DRAG_SRC, "drag", n_y=2, n_extra=1, args_bytes=40, n_events=3)
+    rng = np.random.default_rng(1)
+    B = 64
+    y0 = np.stack([rng.uniform(-1.5, 1.5, B), rng.uniform(-1, 1, B)], 1)
+    args = np.stack([np.ones(B), np.ones(B), np.full(B, 9.81), np.full(B, 1.5), rng.uniform(2.0, 12.0, B)], 1)
+    ev = [c.Event(0), c.Event(1, direction=-1), c.Event(2, terminal=True)]
+    r = c.cysolve_ivp_batch(u, (0.0, 10.0), y0, method="RK45", args=args, rtol=1e-6, atol=1e-8, events=ev, num_extra=1,
+                            dense_output=True)
+    for i in range(0, B, 7):
+        ref = oracle.solve("pendulum_drag", (0.0, 10.0), y0[i], "RK45", 1e-6, 1e-8, args=args[i], dense_output=True,
+                           events=[("y0", 0, None), ("y1", -1, None), ("t_minus_arg4", 0, 1)], fix_quirk11=True,
+                           call_t=[0.1, 0.7, 1.5])
+        v = r[i]
+        assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken)
+        assert [len(t) for t in v.t_events] == [len(t) for t in ref.t_events]
+        assert np.all(np.abs(v.y - ref.y) <= 10 * 1e-6 * np.abs(ref.y) + 10 * 1e-8)
+        assert np.allclose(v(np.array([0.1, 0.7, 1.5])), ref.dense, rtol=1e-5, atol=1e-7)
