@@ -141,6 +141,8 @@ struct PinBuf {
 struct Handle {
     int device = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_comp2 = nullptr;      // pipelined host-I/O path
+    std::vector<cudaEvent_t> ev_pool;                                        // per-chunk events, grown on demand
     cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
     // problem of the last solve
     int rhs_id = -1, method = 0, fp_mode = 0;
@@ -175,6 +177,9 @@ struct Handle {
         if (stream) destroy_cuda();
         CU_TRY(cudaSetDevice(dev));
         CU_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&s_comp2, cudaStreamNonBlocking));
         CU_TRY(cudaEventCreate(&ev_begin));
         CU_TRY(cudaEventCreate(&ev_k0));
         CU_TRY(cudaEventCreate(&ev_k1));
@@ -197,9 +202,23 @@ struct Handle {
         if (ev_k1) cudaEventDestroy(ev_k1);
         if (ev_end) cudaEventDestroy(ev_end);
         if (stream) cudaStreamDestroy(stream);
+        if (s_h2d) cudaStreamDestroy(s_h2d);
+        if (s_d2h) cudaStreamDestroy(s_d2h);
+        if (s_comp2) cudaStreamDestroy(s_comp2);
+        for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+        ev_pool.clear();
         ev_begin = ev_k0 = ev_k1 = ev_end = nullptr;
-        stream = nullptr;
+        stream = s_h2d = s_d2h = s_comp2 = nullptr;
         device = -1;
+    }
+    int events(size_t n)
+    {
+        while (ev_pool.size() < n) {
+            cudaEvent_t e;
+            CU_TRY(cudaEventCreate(&e));
+            ev_pool.push_back(e);
+        }
+        return 0;
     }
     ~Handle() { destroy_cuda(); }
 };
@@ -311,6 +330,113 @@ static int device_sm_count(int dev)
     return n;
 }
 
+// Host-I/O fast path for the final-state variant: the batch is cut into chunks that flow through
+//   copy-in stream  ->  two alternating compute streams  ->  copy-out stream
+// so PCIe traffic hides behind the solve kernels, and the tail of one chunk's persistent kernel overlaps the head of the
+// next (they run on different streams).  Results are identical to the single-launch path: trajectories are independent.
+static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* pe, BatchParams p, int grid, bool use_prep)
+{
+    const size_t B = a.n_traj, NY = pe->ny, NDY = pe->ny + pe->nextra;
+    const size_t args_stride = (size_t)pe->nargs_dbl * sizeof(double);
+    size_t chunk = std::max<size_t>(size_t(1) << 20, (B + 15) / 16);
+    const size_t nchunk = (B + chunk - 1) / chunk;
+    if (h->events(4 * nchunk)) return -1;
+    if (h->d_y0.ensure(B * NY * 8) || h->d_queue.ensure(8 * nchunk)) return -1;
+    if (use_prep && h->d_prep.ensure(B * (NDY + 2) * 8)) return -1;
+    if (h->h_status.ensure(B * 4) || h->h_size.ensure(B * 4) || h->h_steps.ensure(B * 4) || h->h_nrej.ensure(B * 4) ||
+        h->h_nfev.ensure(B * 4) || h->h_tlast.ensure(B * 8) || h->h_ylast.ensure(B * NDY * 8))
+        return -1;
+    const bool per_traj_args = a.n_args > 1 && pe->nargs_dbl > 0;
+    const bool per_traj_span = a.n_t_span > 1;
+    // shared inputs once, on the copy-in stream
+    CU_TRY(cudaEventRecord(h->ev_begin, h->s_h2d));
+    const char* args_src = a.args;
+    if (pe->nargs_dbl > 0) {
+        const size_t n_blobs = per_traj_args ? B : 1;
+        if (h->d_args.ensure(n_blobs * args_stride)) return -1;
+        if (a.n_args == 0 || a.args_len != args_stride) {          // repack (zero padded) through pinned staging
+            if (h->h_stage.ensure(n_blobs * args_stride)) return -1;
+            char* st = h->h_stage.as<char>();
+            memset(st, 0, n_blobs * args_stride);
+            if (a.n_args >= 1)
+                for (size_t i = 0; i < n_blobs; i++) memcpy(st + i * args_stride, a.args + i * a.args_len, a.args_len);
+            args_src = st;
+        }
+        if (!per_traj_args) {
+            CU_TRY(cudaMemcpyAsync(h->d_args.p, args_src, args_stride, cudaMemcpyHostToDevice, h->s_h2d));
+            h->h2d_bytes += args_stride;
+        }
+    } else if (h->d_args.ensure(8)) return -1;
+    if (h->d_tspan.ensure(a.n_t_span * 16)) return -1;
+    if (!per_traj_span) {
+        CU_TRY(cudaMemcpyAsync(h->d_tspan.p, a.t_span, 16, cudaMemcpyHostToDevice, h->s_h2d));
+        h->h2d_bytes += 16;
+    }
+    CU_TRY(cudaMemsetAsync(h->d_queue.p, 0, 8 * nchunk, h->s_h2d));
+    p.args_stride = per_traj_args ? (unsigned)args_stride : 0u;
+    p.t_span_stride = per_traj_span ? 2u : 0u;
+    h->in_y0 = h->d_y0.as<double>(); h->in_args = h->d_args.as<char>(); h->in_tspan = h->d_tspan.as<double>();
+    h->tspan_stride = p.t_span_stride; h->args_stride = p.args_stride;
+
+    for (size_t c = 0; c < nchunk; c++) {
+        const size_t off = c * chunk, n = std::min(chunk, B - off);
+        cudaEvent_t e_in = h->ev_pool[4 * c], e_k0 = h->ev_pool[4 * c + 1], e_k1 = h->ev_pool[4 * c + 2];
+        cudaStream_t sc = (c & 1) ? h->s_comp2 : h->stream;
+        // ---- copy in
+        CU_TRY(cudaMemcpyAsync(h->d_y0.as<double>() + off * NY, a.y0 + off * NY, n * NY * 8, cudaMemcpyHostToDevice, h->s_h2d));
+        h->h2d_bytes += n * NY * 8;
+        if (per_traj_args) {
+            CU_TRY(cudaMemcpyAsync(h->d_args.as<char>() + off * args_stride, args_src + off * args_stride, n * args_stride,
+                                   cudaMemcpyHostToDevice, h->s_h2d));
+            h->h2d_bytes += n * args_stride;
+        }
+        if (per_traj_span) {
+            CU_TRY(cudaMemcpyAsync(h->d_tspan.as<double>() + off * 2, a.t_span + off * 2, n * 16, cudaMemcpyHostToDevice, h->s_h2d));
+            h->h2d_bytes += n * 16;
+        }
+        CU_TRY(cudaEventRecord(e_in, h->s_h2d));
+        // ---- solve
+        BatchParams q = p;
+        q.n_traj = n;
+        q.y0 = h->d_y0.as<double>() + off * NY;
+        q.args = h->d_args.as<char>() + (per_traj_args ? off * args_stride : 0);
+        q.t_span = h->d_tspan.as<double>() + (per_traj_span ? off * 2 : 0);
+        q.status = p.status + off; q.size = p.size + off; q.steps_taken = p.steps_taken + off;
+        q.n_rejected = p.n_rejected + off; q.nfev = p.nfev + off; q.t_last = p.t_last + off; q.y_last = p.y_last + off * NDY;
+        q.queue = h->d_queue.as<unsigned long long>() + c;
+        const int cgrid = (int)std::min<unsigned long long>((unsigned long long)grid, (n + g_opt_block - 1) / g_opt_block);
+        CU_TRY(cudaStreamWaitEvent(sc, e_in, 0));
+        CU_TRY(cudaEventRecord(e_k0, sc));
+        if (use_prep) {
+            double* pr = h->d_prep.as<double>() + off * (NDY + 2);
+            const int pgrid = (int)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)device_sm_count(h->device) * 16);
+            if (pe->prep(a.method, q, pr, pgrid, 256, sc) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("prep kernel launch failed"); return -1; }
+            q.prep = pr;
+            h->launches++;
+        }
+        if (pe->launch(a.method, VAR_LEAN, q, cgrid, g_opt_block, sc) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("solve kernel launch failed"); return -1; }
+        h->launches++;
+        CU_TRY(cudaEventRecord(e_k1, sc));
+        // ---- copy out
+        CU_TRY(cudaStreamWaitEvent(h->s_d2h, e_k1, 0));
+#define D2H(host, dev, T, per) CU_TRY(cudaMemcpyAsync(h->host.as<T>() + off * (per), h->dev.as<T>() + off * (per), n * (per) * sizeof(T), cudaMemcpyDeviceToHost, h->s_d2h)); h->d2h_bytes += n * (per) * sizeof(T)
+        D2H(h_status, d_status, int, 1); D2H(h_size, d_size, unsigned, 1); D2H(h_steps, d_steps, unsigned, 1);
+        D2H(h_nrej, d_nrej, unsigned, 1); D2H(h_nfev, d_nfev, unsigned, 1); D2H(h_tlast, d_tlast, double, 1);
+        D2H(h_ylast, d_ylast, double, NDY);
+#undef D2H
+    }
+    CU_TRY(cudaEventRecord(h->ev_end, h->s_d2h));
+    CU_TRY(cudaStreamSynchronize(h->s_d2h));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    CU_TRY(cudaStreamSynchronize(h->s_comp2));
+    float ms = 0.f, k = 0.f;
+    for (size_t c = 0; c < nchunk; c++) { cudaEventElapsedTime(&ms, h->ev_pool[4 * c + 1], h->ev_pool[4 * c + 2]); k += ms; }
+    h->kernel_ms = k;          // sum of per-chunk kernel spans (they overlap a little across the two compute streams)
+    cudaEventElapsedTime(&h->total_ms, h->ev_begin, h->ev_end);
+    h->row_cap = h->dense_cap = h->ev_cap = 0;
+    return 0;
+}
+
 // The thread-per-trajectory path.  Returns 0 / -1.
 static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
 {
@@ -354,6 +480,39 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     p.refill_min = g_opt_refill_min > 0 ? std::min(32, g_opt_refill_min) : (use_prep ? 1 : 4);
 
     CU_TRY(cudaEventRecord(h->ev_begin, h->stream));
+
+    // ---- per-trajectory outputs
+    if (h->d_status.ensure(B * 4) || h->d_size.ensure(B * 4) || h->d_steps.ensure(B * 4) || h->d_nrej.ensure(B * 4) ||
+        h->d_nfev.ensure(B * 4) || h->d_tlast.ensure(B * 8) || h->d_ylast.ensure(B * NDY * 8) || h->d_queue.ensure(8))
+        return -1;
+    p.status = h->d_status.as<int>();
+    p.size = h->d_size.as<unsigned>();
+    p.steps_taken = h->d_steps.as<unsigned>();
+    p.n_rejected = h->d_nrej.as<unsigned>();
+    p.nfev = h->d_nfev.as<unsigned>();
+    p.t_last = h->d_tlast.as<double>();
+    p.y_last = h->d_ylast.as<double>();
+    p.queue = h->d_queue.as<unsigned long long>();
+
+    int grid = 0;
+    {
+        int ctas = g_opt_ctas_per_sm;
+        if (ctas <= 0) {
+            if (pe->occupancy(a.method, variant, &ctas, g_opt_block) != cudaSuccess) {
+                if (g_last_error.empty()) set_error("occupancy query failed for %s", pe->name(a.method, variant));
+                cudaGetLastError();
+                return -1;
+            }
+            if (ctas <= 0) { set_error("kernel %s cannot be resident with %d threads per CTA", pe->name(a.method, variant), g_opt_block); return -1; }
+        }
+        grid = device_sm_count(h->device) * ctas;
+        const unsigned long long need = (B + g_opt_block - 1) / g_opt_block;
+        if ((unsigned long long)grid > need) grid = (int)std::max<unsigned long long>(need, 1);
+    }
+
+    // ---- host buffers + final-state variant + a batch worth cutting up: pipelined copy/compute path
+    if (!device_io && variant == VAR_LEAN && B >= (size_t(1) << 21))
+        return solve_lean_pipelined(h, a, pe, p, grid, use_prep);
 
     // ---- inputs
     const size_t args_stride = (size_t)pe->nargs_dbl * sizeof(double);
@@ -427,39 +586,10 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         p.n_t_eval = (unsigned)a.n_t_eval;
     }
 
-    // ---- per-trajectory outputs
-    if (h->d_status.ensure(B * 4) || h->d_size.ensure(B * 4) || h->d_steps.ensure(B * 4) || h->d_nrej.ensure(B * 4) ||
-        h->d_nfev.ensure(B * 4) || h->d_tlast.ensure(B * 8) || h->d_ylast.ensure(B * NDY * 8) || h->d_queue.ensure(8))
-        return -1;
-    p.status = h->d_status.as<int>();
-    p.size = h->d_size.as<unsigned>();
-    p.steps_taken = h->d_steps.as<unsigned>();
-    p.n_rejected = h->d_nrej.as<unsigned>();
-    p.nfev = h->d_nfev.as<unsigned>();
-    p.t_last = h->d_tlast.as<double>();
-    p.y_last = h->d_ylast.as<double>();
-    p.queue = h->d_queue.as<unsigned long long>();
-
     size_t row_cap = 0, dense_cap = 0, ev_cap = 0;
     if (want_rows) row_cap = a.n_t_eval ? a.n_t_eval : (a.expected_size ? a.expected_size : 256);
     if (dense) dense_cap = a.expected_size ? a.expected_size + 1 : 257;
     if (a.n_events) ev_cap = a.expected_size ? a.expected_size : 64;
-
-    int grid = 0;
-    {
-        int ctas = g_opt_ctas_per_sm;
-        if (ctas <= 0) {
-            if (pe->occupancy(a.method, variant, &ctas, g_opt_block) != cudaSuccess) {
-                if (g_last_error.empty()) set_error("occupancy query failed for %s", pe->name(a.method, variant));
-                cudaGetLastError();
-                return -1;
-            }
-            if (ctas <= 0) { set_error("kernel %s cannot be resident with %d threads per CTA", pe->name(a.method, variant), g_opt_block); return -1; }
-        }
-        grid = device_sm_count(h->device) * ctas;
-        const unsigned long long need = (B + g_opt_block - 1) / g_opt_block;
-        if ((unsigned long long)grid > need) grid = (int)std::max<unsigned long long>(need, 1);
-    }
 
     for (int pass = 0; pass < 2; pass++) {
         if (want_rows) {
