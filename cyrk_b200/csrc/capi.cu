@@ -85,6 +85,7 @@ void registry_init()
 static int g_opt_refill_min = 0;      // 0 = automatic (1 with prep, 4 without)
 static int g_opt_prep = -1;           // -1 = automatic (n_traj >= 2 Mi), 1 = always, 0 = never
 static int g_opt_block = 128;
+static int g_opt_root_batch = 12;     // measured: 8..16 is the flat optimum on the C3 workload (profiles/r01_notes.md)
 static int g_opt_ctas_per_sm = 0;
 
 // ------------------------------------------------------------------------------------------------
@@ -429,9 +430,11 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
     CU_TRY(cudaStreamSynchronize(h->s_d2h));
     CU_TRY(cudaStreamSynchronize(h->stream));
     CU_TRY(cudaStreamSynchronize(h->s_comp2));
+    // kernel time = span from the first chunk's first launch to the last kernel's end (chunks overlap across the two
+    // compute streams, so summing per-chunk spans would double count)
     float ms = 0.f, k = 0.f;
-    for (size_t c = 0; c < nchunk; c++) { cudaEventElapsedTime(&ms, h->ev_pool[4 * c + 1], h->ev_pool[4 * c + 2]); k += ms; }
-    h->kernel_ms = k;          // sum of per-chunk kernel spans (they overlap a little across the two compute streams)
+    for (size_t c = 0; c < nchunk; c++) { cudaEventElapsedTime(&ms, h->ev_pool[1], h->ev_pool[4 * c + 2]); k = std::max(k, ms); }
+    h->kernel_ms = k;
     cudaEventElapsedTime(&h->total_ms, h->ev_begin, h->ev_end);
     h->row_cap = h->dense_cap = h->ev_cap = 0;
     return 0;
@@ -476,6 +479,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         p.ev_dir[e] = a.event_dirs ? a.event_dirs[e] : 0;
         p.ev_max[e] = a.event_max ? (unsigned long long)a.event_max[e] : ~0ull;
     }
+    p.root_batch = std::min(32, std::max(1, g_opt_root_batch));
     const bool use_prep = g_opt_prep < 0 ? (B >= (size_t(1) << 21)) : (g_opt_prep != 0);
     p.refill_min = g_opt_refill_min > 0 ? std::min(32, g_opt_refill_min) : (use_prep ? 1 : 4);
 
@@ -1135,6 +1139,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "block")) { if (value < 32 || value > 1024 || value % 32) { set_error("block must be a multiple of 32 in [32,1024]"); return -1; } g_opt_block = value; return 0; }
     if (!strcmp(name, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }
     if (!strcmp(name, "prep")) { g_opt_prep = value; return 0; }
+    if (!strcmp(name, "root_batch")) { g_opt_root_batch = value; return 0; }
     set_error("unknown option '%s'", name);
     return -1;
 }

@@ -99,6 +99,7 @@ struct BatchParams {
     const double* prep;          // [n_traj][NDY+2] start-up state from rk_prep_kernel, or NULL (set up inline)
     unsigned long long* queue;   // global work counter (zeroed before launch)
     int       refill_min;        // refill a warp when at least this many lanes are idle (1..32)
+    int       root_batch;        // run the event root search when this many lanes of a warp wait for it (1..32)
 };
 
 // Post-hoc dense evaluation (CySolverResult::call_vectorize, cysolution.cpp:511-616).
