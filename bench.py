@@ -37,6 +37,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# DRAM traffic per launch of the dominant kernel from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum),
+# same workload/batch as the bench line: profiles/r01_ncu_c5_lv_rk45_final.txt (468.3 MB read + 390.1 MB written).
+NCU_TRAFFIC_BYTES = {"C5": 858.4e6}
+
 # F_attempt(m) = n_y*c_m + E_m*F_rhs + s   
 C_M = {"RK23": 25, "RK45": 62, "DOP853": 167}
 E_M = {"RK23": 3, "RK45": 6, "DOP853": 12}
@@ -297,7 +301,9 @@ def main():
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak if fp64_peak and fp64_peak > 0 else None, "traffic": None,
+                         "frac": achieved_tf / fp64_peak if fp64_peak and fp64_peak > 0 else None,
+                         "traffic": NCU_TRAFFIC_BYTES.get(a.workload) if B == WORKLOADS[a.workload]["batch"] else None,
+                         "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_c5_lv_rk45_final.txt)",
                          "peak_source": "in-run dependent-free DFMA probe (cyrk_b200_measure_fp64_tflops); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "flop_per_attempt": f_attempt, "kernel_ms_per_launch": ker_ms_per_launch,

@@ -7,7 +7,8 @@ B = int(os.environ.get('QB', 1 << 20))
 import torch
 y0 = torch.from_numpy(np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)).cuda()
 args_d = torch.tensor([1.5, 1, 3, 1], dtype=torch.float64, device='cuda'); ts_d = torch.tensor([0., 10.], dtype=torch.float64, device='cuda')
-for prep, refill in ((0, 4), (1, 1)):
+for prep, refill, block in ((1, 1, 128), (1, 1, 64), (1, 1, 256), (1, 1, 96), (1, 1, 192)):
+    c.lib().cyrk_b200_set_option(b'block', block)
     c.lib().cyrk_b200_set_option(b"refill_min", refill)
     try: c.lib().cyrk_b200_set_option(b"prep", prep)
     except Exception: pass
@@ -16,4 +17,4 @@ for prep, refill in ((0, 4), (1, 1)):
         r = c.cysolve_ivp_batch('lotkavolterra', ts_d, y0, method='RK45', args=args_d, rtol=1e-7, atol=1e-9, store='final')
         best = min(best, r.kernel_ms)
     att = int(torch.as_tensor(r.steps_taken, device='cuda').sum().item()) + int(torch.as_tensor(r.n_rejected, device='cuda').sum().item())
-    print(os.environ.get("CYRK_B200_LIB", "default"), f"prep={prep} refill={refill} kernel_ms={best:.3f} attempts={att}", flush=True)
+    print(os.environ.get("CYRK_B200_LIB", "default"), f"prep={prep} refill={refill} block={block} kernel_ms={best:.3f} attempts={att}", flush=True)
