@@ -85,6 +85,8 @@ void registry_init()
 static int g_opt_refill_min = 0;      // 0 = automatic (1 with prep, 4 without)
 static int g_opt_prep = -1;           // -1 = automatic (n_traj >= 2 Mi), 1 = always, 0 = never
 static int g_opt_block = 128;
+static int g_opt_cta_smem_vecs = -1;  // CTA path: working vectors kept in shared memory (-1 = as many as fit)
+static int g_opt_cta_block = 0;       // CTA path: threads per CTA (0 = by n_y)
 static int g_opt_root_batch = 12;     // measured: 8..16 is the flat optimum on the C3 workload (profiles/r01_notes.md)
 static int g_opt_ctas_per_sm = 0;
 
@@ -770,10 +772,19 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     const int nvec = cta_num_vectors(a.method);
     const size_t vec_bytes = (size_t)p.n_pad * 8;
     size_t fit = ((size_t)optin - 1024) / vec_bytes;
-    p.n_smem_vec = (unsigned)std::min<size_t>(fit, (size_t)nvec);
+    int smem_per_sm = 0;
+    CU_TRY(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
+    // Measured (profiles/r01_notes.md, n_y = 4096): where the stage vectors live (shared memory vs the L2-resident
+    // slab) changes the kernel time by < 2 %, but TWO 512-thread CTAs per SM beat one 1024-thread CTA by 10 %
+    // (one CTA's barrier waits hide behind the other's arithmetic).  So: 512 threads, and only as many vectors in
+    // shared memory as still leave room for two CTAs per SM.
+    int block = N <= 256 ? 128 : N <= 1024 ? 256 : 512;
+    if (g_opt_cta_block > 0) block = g_opt_cta_block;
+    const size_t fit2 = ((size_t)smem_per_sm / 2 > 2048 + vec_bytes) ? ((size_t)smem_per_sm / 2 - 2048) / vec_bytes : 0;
+    p.n_smem_vec = (unsigned)std::min<size_t>({fit, fit2, (size_t)nvec});
+    if (g_opt_cta_smem_vecs >= 0) p.n_smem_vec = std::min<unsigned>((unsigned)std::min<size_t>(fit, (size_t)nvec), (unsigned)g_opt_cta_smem_vecs);
     const size_t smem = (size_t)p.n_smem_vec * vec_bytes;
-    const int block = N <= 256 ? 128 : N <= 1024 ? 256 : N <= 2048 ? 512 : 1024;
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)(2048 / block), ((size_t)optin) / (smem + 2048)}));
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)(2048 / block), ((size_t)smem_per_sm) / (smem + 2048)}));
     int grid = (int)std::min<unsigned long long>((unsigned long long)device_sm_count(h->device) * per_sm, B);
     const size_t n_glob = (size_t)nvec - p.n_smem_vec;
     if (h->d_scratch.ensure((size_t)grid * (n_glob + 2) * vec_bytes)) return -1;
@@ -1140,6 +1151,8 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }
     if (!strcmp(name, "prep")) { g_opt_prep = value; return 0; }
     if (!strcmp(name, "root_batch")) { g_opt_root_batch = value; return 0; }
+    if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
+    if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
     set_error("unknown option '%s'", name);
     return -1;
 }
