@@ -5,6 +5,7 @@ ctypes binding of the C ABI (_lib.py) and the CUDA sources (csrc/).  There is no
 """
 from ._lib import CyrkB200Error, LIB_PATH, SIGNATURES, last_error, lib, status_message  # noqa: F401
 from .solver import (  # noqa: F401
-    BatchResult, Event, TrajectoryView, UserRHS, cysolve_ivp_batch, find_ode_method_int, EVENT_IDS)
+    BatchResult, Event, TrajectoryView, UserRHS, cysolve_ivp_batch, find_ode_method_int, EVENT_IDS,
+    interpolate_from_solution_list)
 
 __version__ = "0.1.0"

@@ -430,3 +430,30 @@ def cysolve_ivp_batch(
         if not h:
             raise CyrkB200Error(_lib.last_error())
     return BatchResult(h, method_int, keep_inputs=keep, device_io=device_io)
+
+
+def interpolate_from_solution_list(t, solutions: Sequence[BatchResult], breakpoints: Sequence[float]):
+    """Batched analogue of ``interpolate_from_solution_list`` (CyRK/cy/helpers.pyx:5-34): several dense batch solutions
+    over consecutive spans are evaluated on one time grid.  ``breakpoints[k]`` is the upper time bound of
+    ``solutions[k]`` (ascending ``t``); a point is handed to the next solution once it EXCEEDS the current breakpoint,
+    exactly like the reference loop.  Returns ``out[B, len(t), num_dy]`` and the per-trajectory call codes."""
+    ts = np.ascontiguousarray(np.atleast_1d(t), dtype=np.float64)
+    if len(solutions) != len(breakpoints) or not solutions:
+        raise ValueError("one breakpoint per solution is required")
+    B, ndy = solutions[0].n_traj, solutions[0].num_dy
+    out = np.full((B, ts.size, ndy), np.nan)
+    codes = np.zeros(B, dtype=np.int32)
+    owner = np.zeros(ts.size, dtype=np.int64)
+    k = 0
+    for i, x in enumerate(ts):                       # same sequential hand-over rule as the reference
+        while x > breakpoints[k] and k + 1 < len(solutions):
+            k += 1
+        owner[i] = k
+    for k, sol in enumerate(solutions):
+        sel = np.nonzero(owner == k)[0]
+        if sel.size == 0:
+            continue
+        o, c = sol.call(ts[sel])
+        out[:, sel, :] = o
+        codes = np.where(codes != 0, codes, c)
+    return out, codes

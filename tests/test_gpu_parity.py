@@ -302,3 +302,17 @@ def test_pipelined_host_path_equals_device_resident_path():
         d = torch.as_tensor(getattr(dev, name), device="cuda").cpu().numpy()
         assert np.array_equal(np.asarray(getattr(host, name)), d, equal_nan=True), name
     assert (host.status == 1).all() and np.array_equal(host.t_last, ts[:, 1])
+
+
+def test_interpolate_from_solution_list(oracle):
+    """helpers.pyx:5-34 analogue: two dense solves over consecutive spans, one query grid."""
+    y0 = np.array([[10.0, 5.0], [12.0, 4.0]])
+    kw = dict(method="RK45", args=[1.5, 1, 3, 1], rtol=1e-8, atol=1e-10, dense_output=True)
+    a = c.cysolve_ivp_batch("lotkavolterra", (0.0, 5.0), y0, **kw)
+    b = c.cysolve_ivp_batch("lotkavolterra", (5.0, 10.0), np.array(a.y_last), **kw)
+    t = np.linspace(0.0, 10.0, 41)
+    out, codes = c.interpolate_from_solution_list(t, [a, b], [5.0, 10.0])
+    assert (codes == 0).all() and out.shape == (2, 41, 2)
+    for i in range(2):
+        ref = oracle.solve("lotkavolterra", (0.0, 10.0), y0[i], "RK45", 1e-10, 1e-12, args=[1.5, 1, 3, 1], dense_output=True, call_t=t)
+        assert np.allclose(out[i].T, ref.dense, rtol=1e-6, atol=1e-8)
