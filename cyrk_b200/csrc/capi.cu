@@ -449,7 +449,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     const bool device_io = (a.flags & CYRK_FLAG_DEVICE_IO) != 0;
     const bool want_rows = a.store_mode == CYRK_STORE_ROWS;
     const bool dense = a.dense_output != 0;
-    const int variant = (dense || a.n_events > 0) ? VAR_FULL : ((want_rows || a.n_t_eval > 0) ? VAR_ROWS : VAR_LEAN);
+    const int variant = a.n_events > 0 ? VAR_FULL : ((dense || want_rows || a.n_t_eval > 0) ? VAR_ROWS : VAR_LEAN);
     const int q_order = a.method == CYRK_METHOD_RK23 ? 3 : a.method == CYRK_METHOD_RK45 ? 4 : 7;
 
     h->ny = NY; h->nx = NX; h->ndy = NDY; h->q_order = q_order;

@@ -41,8 +41,8 @@ enum Method : int { METHOD_RK23 = 3, METHOD_RK45 = 4, METHOD_DOP853 = 5 };
 // Kernel feature variants (compile-time): what one trajectory may produce besides its last row.
 enum Variant : int {
     VAR_LEAN = 0,   // final row + counters only: no t_eval, no dense store, no events, no row store
-    VAR_ROWS = 1,   // + row store (every accepted step, or the t_eval samples)
-    VAR_FULL = 2,   // + dense-interpolant store + events
+    VAR_ROWS = 1,   // + row store (every accepted step, or the t_eval samples) + dense-interpolant store
+    VAR_FULL = 2,   // + events
     VAR_COUNT = 3
 };
 

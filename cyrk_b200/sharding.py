@@ -76,3 +76,37 @@ def ensemble_reduce(y_last, ok, group=None, device=None):
     mean = out[:ndy] / cnt
     var = out[ndy:2 * ndy] / cnt - mean * mean
     return mean, var, int(cnt)
+
+
+def solve_on_devices(diffeq, t_span, y0, devices, args=None, **kw):
+    """Drive several GPUs from ONE process: one host thread (and one stream, owned by its result handle) per
+    device, contiguous shards, no communication.  The C entry points release nothing Python-side (ctypes drops the
+    GIL for the duration of a call), so the shards run concurrently.  Returns a list of (lo, hi, BatchResult).
+
+    This is the in-process alternative to one-process-per-GPU (bench.py / torchrun); both use the same sharding."""
+    import threading
+    from .solver import cysolve_ivp_batch
+    y0 = np.asarray(y0, dtype=np.float64)
+    n = y0.shape[0]
+    world = len(devices)
+    out = [None] * world
+    errs = [None] * world
+
+    def work(r):
+        lo, hi = shard_bounds(n, r, world)
+        try:
+            res = cysolve_ivp_batch(diffeq, _slice_per_traj(t_span, lo, hi, n), y0[lo:hi],
+                                    args=_slice_per_traj(args, lo, hi, n), device=int(devices[r]), **kw)
+            out[r] = (lo, hi, res)
+        except Exception as e:          # re-raised in the caller's thread
+            errs[r] = e
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errs:
+        if e is not None:
+            raise e
+    return out

@@ -316,3 +316,20 @@ def test_interpolate_from_solution_list(oracle):
     for i in range(2):
         ref = oracle.solve("lotkavolterra", (0.0, 10.0), y0[i], "RK45", 1e-10, 1e-12, args=[1.5, 1, 3, 1], dense_output=True, call_t=t)
         assert np.allclose(out[i].T, ref.dense, rtol=1e-6, atol=1e-8)
+
+
+def test_in_process_multi_device_sharding():
+    """One process driving several devices with host threads (here: the same device twice, which exercises two
+    concurrent handles/streams).  The stitched result must equal the single-call result bit for bit."""
+    from cyrk_b200.sharding import solve_on_devices
+    rng = np.random.default_rng(21)
+    B = 30001
+    y0 = np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)
+    args = np.stack([rng.uniform(1.4, 1.6, B), np.ones(B), np.full(B, 3.0), np.ones(B)], 1)
+    kw = dict(method="RK45", rtol=1e-6, atol=1e-8, store="final")
+    whole = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, args=args, **kw)
+    parts = solve_on_devices("lotkavolterra", (0.0, 10.0), y0, devices=[0, 0, 0], args=args, **kw)
+    assert [p[0] for p in parts] == [0, 10001, 20001] and parts[-1][1] == B
+    y = np.concatenate([np.array(p[2].y_last) for p in parts])
+    st = np.concatenate([np.array(p[2].steps_taken) for p in parts])
+    assert np.array_equal(y, whole.y_last) and np.array_equal(st, whole.steps_taken)
