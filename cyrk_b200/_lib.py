@@ -67,6 +67,7 @@ SIGNATURES = {
     "cyrk_b200_get_num_interpolates_capacity": (C.c_size_t, [C.c_void_p]),
     "cyrk_b200_get_num_interpolates_ptr": (C.c_void_p, [C.c_void_p]),
     "cyrk_b200_call_vectorize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "cyrk_b200_ensemble_sums": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cyrk_b200_get_kernel_ms": (C.c_double, [C.c_void_p]),
     "cyrk_b200_get_total_ms": (C.c_double, [C.c_void_p]),
     "cyrk_b200_get_launch_count": (C.c_uint, [C.c_void_p]),

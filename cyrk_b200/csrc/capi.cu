@@ -894,6 +894,47 @@ static int solve_impl(Handle* h, const SolveArgs& a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Ensemble sums: per-CTA partials in a fixed order, then one CTA folds the partials (deterministic).
+// ------------------------------------------------------------------------------------------------
+__global__ void ensemble_partial_kernel(const int* __restrict__ status, const double* __restrict__ y_last,
+                                        unsigned long long n, int ndy, double* __restrict__ partial)
+{
+    extern __shared__ double sh[];          // [blockDim.x / 32][2 * ndy + 1]
+    const int nv = 2 * ndy + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const unsigned long long per = (n + gridDim.x - 1) / gridDim.x;
+    const unsigned long long lo = (unsigned long long)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+    for (int v = 0; v < nv; v++) {
+        double acc = 0.0;
+        for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const int st = status[i];
+            if (st == 1 || st == 2) {
+                if (v == 2 * ndy) acc += 1.0;
+                else { const double y = y_last[i * ndy + (v % ndy)]; acc += v < ndy ? y : y * y; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) sh[warp * nv + v] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < nv) {
+        double acc = 0.0;
+        for (int w = 0; w < nwarp; w++) acc += sh[w * nv + threadIdx.x];
+        partial[(size_t)blockIdx.x * nv + threadIdx.x] = acc;
+    }
+}
+
+__global__ void ensemble_final_kernel(const double* __restrict__ partial, int nblocks, int nv, double* __restrict__ out)
+{
+    if ((int)threadIdx.x < nv) {
+        double acc = 0.0;
+        for (int b = 0; b < nblocks; b++) acc += partial[(size_t)b * nv + threadIdx.x];
+        out[threadIdx.x] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 throughput probe: 8 independent DFMA chains per thread
 // ------------------------------------------------------------------------------------------------
 __global__ void fp64_probe_kernel(double* out, int iters, double a, double b)
@@ -1133,6 +1174,27 @@ int cyrk_b200_call_vectorize(void* hv, const double* t, size_t n_t, double* out,
         CU_TRY(cudaMemcpyAsync(out, d_out, B * n_t * NDY * 8, cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaMemcpyAsync(codes, q.code, B * 4, cudaMemcpyDeviceToHost, h->stream));
     }
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int cyrk_b200_ensemble_sums(void* hv, double* out)
+{
+    Handle* h = H(hv);
+    if (!h || !h->solved) { set_error("handle holds no solution"); return -1; }
+    if (!out) { set_error("out is NULL"); return -1; }
+    const int ndy = (int)h->ndy, nv = 2 * ndy + 1;
+    if (nv > 256) { set_error("ensemble sums support num_dy <= 127"); return -1; }
+    CU_TRY(cudaSetDevice(h->device));
+    const int block = 256, grid = std::max(1, std::min(device_sm_count(h->device) * 4, (int)((h->n_traj + block - 1) / block)));
+    if (h->d_scratch.ensure((size_t)(grid + 1) * nv * 8)) return -1;
+    double* partial = h->d_scratch.as<double>();
+    double* dout = h->device_io ? out : partial + (size_t)grid * nv;
+    ensemble_partial_kernel<<<grid, block, (block / 32) * nv * sizeof(double), h->stream>>>(
+        h->d_status.as<int>(), h->d_ylast.as<double>(), h->n_traj, ndy, partial);
+    ensemble_final_kernel<<<1, 256, 0, h->stream>>>(partial, grid, nv, dout);
+    CU_TRY(cudaGetLastError());
+    if (!h->device_io) CU_TRY(cudaMemcpyAsync(out, dout, nv * 8, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }

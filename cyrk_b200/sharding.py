@@ -56,6 +56,24 @@ def solve_sharded(solve_fn: Callable, diffeq, t_span, y0, args=None, group=None,
     return local, gathered
 
 
+def ensemble_reduce_from_sums(sum_y, sum_y2, count, group=None, device=None):
+    """Second half of the ensemble reduction: all-reduce(SUM) of the (2*n_dy + 1) local sums -- e.g. the ones
+    BatchResult.ensemble_sums() computed on the device -- and turn them into (mean, var, count)."""
+    import torch
+    import torch.distributed as dist
+    buf = np.concatenate([np.asarray(sum_y, dtype=np.float64), np.asarray(sum_y2, dtype=np.float64), [float(count)]])
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    out = t.cpu().numpy()
+    ndy = (out.size - 1) // 2
+    cnt = out[-1]
+    mean = out[:ndy] / cnt
+    return mean, out[ndy:2 * ndy] / cnt - mean * mean, int(cnt)
+
+
 def ensemble_reduce(y_last, ok, group=None, device=None):
     """Ensemble mean / variance of the final states over ALL ranks: local sums, then one all-reduce(SUM) of
     (2*n_dy + 1) float64 values.  Returns (mean[n_dy], var[n_dy], count)."""

@@ -273,6 +273,17 @@ class BatchResult:
             raise CyrkB200Error(_lib.last_error())
         return out, codes
 
+    def ensemble_sums(self):
+        """(sum y_last, sum y_last^2, count) over the successful trajectories, reduced on the device in a fixed order
+        (cyrk_b200_ensemble_sums).  All-reduce the concatenation across ranks for a multi-GPU ensemble mean/variance
+        (cyrk_b200.sharding.ensemble_reduce)."""
+        if self.device_io:
+            raise CyrkB200Error("device-resident result: call cyrk_b200_ensemble_sums with a device pointer")
+        out = np.zeros(2 * self.num_dy + 1)
+        if _lib.lib().cyrk_b200_ensemble_sums(self._h, out.ctypes.data) != 0:
+            raise CyrkB200Error(_lib.last_error())
+        return out[:self.num_dy], out[self.num_dy:2 * self.num_dy], int(out[-1])
+
     def close(self):
         if self._h:
             _lib.lib().cyrk_b200_free(self._h)

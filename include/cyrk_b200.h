@@ -195,6 +195,13 @@ const uint32_t* cyrk_b200_get_num_interpolates_ptr(void* h);      /* [n_traj] (d
  * `out`/`codes` are host pointers (device pointers with CYRK_FLAG_DEVICE_IO).  Returns 0 or -1. */
 int cyrk_b200_call_vectorize(void* h, const double* t, size_t n_t, double* out, int32_t* codes);
 
+/* Ensemble sums over the successful trajectories (status 1 or 2) of the last solve, computed on the device with a
+ * fixed-order two-stage reduction: out[0..num_dy) = sum of y_last, out[num_dy..2*num_dy) = sum of y_last^2,
+ * out[2*num_dy] = number of trajectories counted.  This is the local half of the optional ensemble reduction; the
+ * caller all-reduces the 2*num_dy+1 doubles across ranks (NCCL / torch.distributed) -- the only collective this
+ * path ever needs.  `out` is a host pointer (device pointer with CYRK_FLAG_DEVICE_IO).  Returns 0 or -1. */
+int cyrk_b200_ensemble_sums(void* h, double* out);
+
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------- */
 double   cyrk_b200_get_kernel_ms(void* h);      /* CUDA-event time of the solve kernel(s) of the last call */
 double   cyrk_b200_get_total_ms(void* h);       /* CUDA-event time H2D -> kernels -> D2H of the last call   */

@@ -1,4 +1,4 @@
-# cyrk_b200.pxd -- Cython declarations of include/cyrk_b200.h (generated by tools in this repo; see INTEGRATION.md).
+# cyrk_b200.pxd -- Cython declarations of include/cyrk_b200.h (generated from the header; see INTEGRATION.md).
 # `cimport` users call these `nogil`, like cysolve_ivp (CyRK/cy/cysolver_api.pxd:385-407).
 from libc.stdint cimport int32_t, uint32_t
 
@@ -67,6 +67,7 @@ cdef extern from "cyrk_b200.h" nogil:
     size_t cyrk_b200_get_num_interpolates_capacity(void* h)
     const uint32_t* cyrk_b200_get_num_interpolates_ptr(void* h)
     int cyrk_b200_call_vectorize(void* h, const double* t, size_t n_t, double* out, int32_t* codes)
+    int cyrk_b200_ensemble_sums(void* h, double* out)
     double cyrk_b200_get_kernel_ms(void* h)
     double cyrk_b200_get_total_ms(void* h)
     unsigned cyrk_b200_get_launch_count(void* h)

@@ -7,7 +7,7 @@ B = int(os.environ.get('QB', 1 << 20))
 import torch
 y0 = torch.from_numpy(np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)).cuda()
 args_d = torch.tensor([1.5, 1, 3, 1], dtype=torch.float64, device='cuda'); ts_d = torch.tensor([0., 10.], dtype=torch.float64, device='cuda')
-for prep, refill, block in ((1, 1, 128), (1, 1, 64), (1, 1, 256), (1, 1, 96), (1, 1, 192)):
+for prep, refill, block in ((1, 1, 128), (1, 1, 64)):
     c.lib().cyrk_b200_set_option(b'block', block)
     c.lib().cyrk_b200_set_option(b"refill_min", refill)
     try: c.lib().cyrk_b200_set_option(b"prep", prep)

@@ -333,3 +333,17 @@ def test_in_process_multi_device_sharding():
     y = np.concatenate([np.array(p[2].y_last) for p in parts])
     st = np.concatenate([np.array(p[2].steps_taken) for p in parts])
     assert np.array_equal(y, whole.y_last) and np.array_equal(st, whole.steps_taken)
+
+
+def test_device_ensemble_sums_match_numpy_and_are_deterministic():
+    rng = np.random.default_rng(5)
+    B = 100003
+    y0 = np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)
+    r = c.cysolve_ivp_batch("lotkavolterra", (0, 5), y0, method="RK45", args=[1.5, 1, 3, 1], rtol=1e-6, atol=1e-8, store="final",
+                            max_num_steps=60)            # some trajectories fail with -52 and must be left out
+    s1, s2, n = r.ensemble_sums()
+    ok = (r.status == 1) | (r.status == 2)
+    assert 0 < n == int(ok.sum()) < B
+    assert np.allclose(s1, r.y_last[ok].sum(0), rtol=1e-12) and np.allclose(s2, (r.y_last[ok] ** 2).sum(0), rtol=1e-12)
+    t1, t2, m = r.ensemble_sums()
+    assert np.array_equal(s1, t1) and np.array_equal(s2, t2) and m == n      # fixed summation order
