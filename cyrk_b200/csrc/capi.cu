@@ -699,7 +699,8 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     if (a.num_extra != 0) { set_error("the CTA-per-trajectory path does not capture extra outputs yet"); return -1; }
     if (a.n_events != 0) { set_error("the CTA-per-trajectory path does not support events yet"); return -1; }
     if (a.dense_output) { set_error("the CTA-per-trajectory path does not store dense output yet (use t_eval)"); return -1; }
-    if (a.n_args == 0 || a.args_len < 8) { set_error("largey problems need args = (decay_rate, ...)"); return -1; }
+    const bool user_rhs = a.rhs_id >= CYRK_RHS_USER_BASE;
+    if (!user_rhs && (a.n_args == 0 || a.args_len < 8)) { set_error("largey problems need args = (decay_rate, ...)"); return -1; }
     if (N > 0x7fffffffu) { set_error("n_y too large"); return -1; }
     h->ny = N; h->nx = 0; h->ndy = N; h->q_order = 0;
     h->n_traj = B; h->n_events = 0; h->n_t_eval = a.n_t_eval;
@@ -738,7 +739,7 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         p.y0 = a.y0; p.args = a.args; p.t_span = a.t_span;
     } else {
         if (upload(h, h->d_y0, a.y0, B * N * 8)) return -1;
-        if (upload(h, h->d_args, a.args, (a.n_args > 1 ? B : 1) * a.args_len)) return -1;
+        if (upload(h, h->d_args, a.args, a.n_args ? (a.n_args > 1 ? B : 1) * a.args_len : 0)) return -1;
         if (upload(h, h->d_tspan, a.t_span, a.n_t_span * 16)) return -1;
         p.y0 = h->d_y0.as<double>(); p.args = h->d_args.as<char>(); p.t_span = h->d_tspan.as<double>();
     }
@@ -799,7 +800,15 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         }
         CU_TRY(cudaMemsetAsync(h->d_queue.p, 0, 8, h->stream));
         CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
-        CU_TRY((fp == FP_STRICT ? cta_launch_strict : cta_launch_fast)(a.rhs_id, a.method, p, grid, block, smem, h->stream));
+        if (user_rhs) {
+            if (user_rhs_launch_cta(a.rhs_id, a.method, fp == FP_STRICT, h->device, p, grid, block, smem, h->stream) != cudaSuccess) {
+                cudaGetLastError();
+                if (g_last_error.empty()) set_error("user CTA kernel launch failed");
+                return -1;
+            }
+        } else {
+            CU_TRY((fp == FP_STRICT ? cta_launch_strict : cta_launch_fast)(a.rhs_id, a.method, p, grid, block, smem, h->stream));
+        }
         h->launches++;
         CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
         if ((want_rows || !device_io) && download(h, h->h_size, h->d_size, B * 4)) return -1;
@@ -876,6 +885,11 @@ static int solve_impl(Handle* h, const SolveArgs& a)
     Dispatch disp;
     g_last_error.clear();
     if (!make_dispatch(a.rhs_id, fp, a.device, &disp)) { set_error("unknown right-hand side id %d", a.rhs_id); return -1; }
+    if (a.rhs_id >= CYRK_RHS_USER_BASE && disp.ny == 0) {        // user right-hand side registered for large systems
+        if (solve_cta_path(h, a, fp)) return -1;
+        h->solved = true;
+        return 0;
+    }
     const Dispatch* pe = &disp;
     if ((size_t)pe->ny != a.n_y) { set_error("right-hand side %d has n_y = %d but y0 has n_y = %zu", a.rhs_id, pe->ny, a.n_y); return -1; }
     if ((size_t)pe->nextra != a.num_extra) {

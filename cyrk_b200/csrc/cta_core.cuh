@@ -80,7 +80,7 @@ struct CtaSolver {
 
     CYRK_DI double* vecp(int v) const
     {
-        return (unsigned)v < n_smem_vec ? smem_base + (size_t)v * n_pad : slab_base + (size_t)((unsigned)v - n_smem_vec) * n_pad;
+        return (unsigned)v < n_smem_vec ? smem_base + (unsigned long long)v * n_pad : slab_base + (unsigned long long)((unsigned)v - n_smem_vec) * n_pad;
     }
     CYRK_DI double* K(int j) const { return vecp(V_K0 + j); }
 
@@ -369,7 +369,7 @@ struct CtaSolver {
                         // derivative is written to the problem-independent spare slot and copied back.
                         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) in[i] = yo[i] + dot_k<XRow<2>, 15>(i, XRow<2>{}) * step;
                         __syncthreads();
-                        double* spare = aux + (size_t)p.n_pad;
+                        double* spare = aux + (unsigned long long)p.n_pad;
                         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) spare[i] = Prob::eval(i, t_old + (step * LdDop::cx(2)), in, n, args, aux);
                         nfev++;
                         __syncthreads();
@@ -423,7 +423,7 @@ struct CtaSolver {
 };
 
 template <class Prob, int METHOD>
-__global__ void __launch_bounds__(1024, 1) rk_cta_kernel(const CtaParams p)
+CYRK_DI void rk_cta_body(const CtaParams& p)
 {
     using Solver = CtaSolver<Prob, METHOD>;
     extern __shared__ double smem[];
@@ -435,12 +435,12 @@ __global__ void __launch_bounds__(1024, 1) rk_cta_kernel(const CtaParams p)
     S.prepared = false;
     // working vectors: the first n_smem_vec in shared memory, the rest in this CTA's L2-resident slab
     const unsigned n_glob = Solver::NVEC > p.n_smem_vec ? Solver::NVEC - p.n_smem_vec : 0u;
-    double* slab = p.scratch + (size_t)blockIdx.x * (size_t)(n_glob + 2) * p.n_pad;
+    double* slab = p.scratch + (unsigned long long)blockIdx.x * (unsigned long long)(n_glob + 2) * p.n_pad;
     S.smem_base = smem;
     S.slab_base = slab;
     S.n_pad = p.n_pad;
     S.n_smem_vec = p.n_smem_vec;
-    S.aux = slab + (size_t)n_glob * p.n_pad;          // aux table [n_pad] followed by one spare vector [n_pad]
+    S.aux = slab + (unsigned long long)n_glob * p.n_pad;          // aux table [n_pad] followed by one spare vector [n_pad]
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) next_traj = atomicAdd(p.queue, 1ULL);
@@ -449,6 +449,12 @@ __global__ void __launch_bounds__(1024, 1) rk_cta_kernel(const CtaParams p)
         if (traj >= p.n_traj) break;
         S.solve(p, traj);
     }
+}
+
+template <class Prob, int METHOD>
+__global__ void __launch_bounds__(1024, 1) rk_cta_kernel(const CtaParams p)
+{
+    rk_cta_body<Prob, METHOD>(p);
 }
 
 }  // namespace CYRK_FP_NS

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstddef>
 #include "cyrk_defs.h"
+#include "cta_core_params.h"
 
 namespace cyrk {
 // Registers (and validates by compiling one kernel) a user right-hand side; returns its id (>= 1000) or -1.
@@ -16,4 +17,8 @@ cudaError_t user_rhs_launch_prep(int rhs_id, int method, bool strict, int device
                                  int block, cudaStream_t s);
 cudaError_t user_rhs_launch_dense(int rhs_id, int method, bool strict, int device, const DenseEvalParams& p, int grid, int block,
                                   cudaStream_t s);
+// Large systems (registered with n_y == 0): the source defines
+//     __device__ double <entry>(unsigned i, double t, const double* y, unsigned n, const char* args);   -> dy_i
+cudaError_t user_rhs_launch_cta(int rhs_id, int method, bool strict, int device, const CtaParams& p, int grid, int block,
+                                size_t smem, cudaStream_t s);
 }  // namespace cyrk

@@ -33,7 +33,7 @@ EVENTS = dict(y0_gt_50=0, y1_lt_50=1, t_gt_5=2, lorenz_t_ge_5=3, lorenz_y_range=
 
 SIZE_MAX = (1 << 64) - 1
 
-DIFFEQ_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_char_p, C.c_void_p)
+DIFFEQ_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_void_p, C.c_void_p)
 
 
 class _Problem(C.Structure):
