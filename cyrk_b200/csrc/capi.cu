@@ -467,6 +467,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         p.atol[i] = a.atols[a.n_atols > 1 ? i : 0];
     }
     p.max_step = a.max_step;
+    p.has_max_step = (a.max_step < std::numeric_limits<double>::infinity()) ? 1 : 0;
     p.first_step = a.first_step;
     {
         int uf; size_t mx;

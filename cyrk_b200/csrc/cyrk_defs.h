@@ -61,6 +61,7 @@ struct BatchParams {
     double rtol[CYRK_MAX_NY];    // already floored at 100*eps on the host (rk.cpp:600-608)
     double atol[CYRK_MAX_NY];
     double max_step;             // INF = none
+    int    has_max_step;         // max_step < INF (lets the kernel test it with a uniform integer compare)
     double first_step;           // 0 = automatic
     unsigned max_num_steps;      // cysolver.cpp:403-410 (RAM cap folded in on the host)
     int    user_max_steps;       // which of -52 / -53 to report

@@ -138,8 +138,15 @@ struct ProbLotkaVolterra {      // cysolver_test.pyx:104-118, Performance/lotkav
         const double* p = reinterpret_cast<const double*>(args);
         const double a = p[0], b = p[1], c = p[2], d = p[3];
         const double y0 = y[0], y1 = y[1];
+#if CYRK_FP_STRICT
         dy[0] = a * y0 - b * y0 * y1;
         dy[1] = -c * y1 + d * y0 * y1;
+#else
+        // production build: the same polynomial factored (2 DFMA + 2 DMUL instead of 2 DFMA + 4 DMUL); the
+        // re-association changes the result by <= 2 ulp, the same order as the FMA contraction itself
+        dy[0] = y0 * fma(-b, y1, a);
+        dy[1] = y1 * fma(d, y0, -c);
+#endif
     }
 };
 
