@@ -283,6 +283,41 @@ static __constant__ StoreRK23 g_store_rk23 = make_store_rk23();
 static __constant__ StoreRK45 g_store_rk45 = make_store_rk45();
 static __constant__ StoreDOP853 g_store_dop853 = make_store_dop853();
 
+
+// ---------------------------------------------------------------------------------------------
+// Step-size controller constants of the production build, also in __constant__ memory.
+// With e2 = NY * err^2 (the un-normalised squared error norm) the reference's
+//     SAFETY * err^(-1/(q+1))  =  0.9 * NY^(1/M) * e2^(-1/M),   M = 2(q+1) = 6, 10, 16
+// and one Newton step r1 = r*((M+1) - e2*r^M)/M from a seed r ~ e2^(-1/M) gives
+//     0.9 * err^(-1/(q+1))  ~=  r * (A - B * e2 * r^M),   A = C(M+1)/M,  B = C/M,  C = 0.9 * NY^(1/M).
+// ---------------------------------------------------------------------------------------------
+CYRK_HD constexpr double const_root(double x, int m)      // x^(1/m), x >= 1, by Newton's method
+{
+    double r = 1.0 + (x - 1.0) / m;
+    for (int it = 0; it < 200; it++) {
+        double pw = 1.0;
+        for (int i = 0; i < m - 1; i++) pw *= r;
+        r = r - (r * pw - x) / (m * pw);
+    }
+    return r;
+}
+struct StoreCtrl { double A[3][CYRK_MAX_NY + 1]; double B[3][CYRK_MAX_NY + 1]; double thresh_rel, thresh_abs; };
+CYRK_HD constexpr StoreCtrl make_store_ctrl()
+{
+    StoreCtrl s{};
+    const int ms[3] = {6, 10, 16};
+    for (int mi = 0; mi < 3; mi++)
+        for (int n = 1; n <= CYRK_MAX_NY; n++) {
+            const double C = 0.9 * const_root((double)n, ms[mi]);
+            s.A[mi][n] = C * (double)(ms[mi] + 1) / (double)ms[mi];
+            s.B[mi][n] = C / (double)ms[mi];
+        }
+    s.thresh_rel = 4.0e-15;
+    s.thresh_abs = 1.0e-300;
+    return s;
+}
+static __constant__ StoreCtrl g_store_ctrl = make_store_ctrl();
+
 template <class Tab> struct TabLd;
 template <> struct TabLd<TabRK23> {
     __device__ __forceinline__ static double c(int s) { return g_store_rk23.c[s]; }
