@@ -20,6 +20,7 @@
 #include "../../include/cyrk_b200.h"
 #include "cyrk_defs.h"
 #include "registry.h"
+#include "rk_core.cuh"
 #include "problems_builtin.cuh"
 #include "cta_solver.h"
 #include "nvrtc_rhs.h"
@@ -87,6 +88,7 @@ static int g_opt_prep = -1;           // -1 = automatic (n_traj >= 2 Mi), 1 = al
 static int g_opt_block = 128;
 static int g_opt_cta_smem_vecs = -1;  // CTA path: working vectors kept in shared memory (-1 = as many as fit)
 static int g_opt_cta_block = 0;       // CTA path: threads per CTA (0 = by n_y)
+static int g_opt_cta_kernel = 0;      // CTA path: 0 = register-resident kernel where it applies, 1 = always the shared-memory/slab kernel
 static int g_opt_root_batch = 12;     // measured: 8..16 is the flat optimum on the C3 workload (profiles/r01_notes.md)
 static int g_opt_ctas_per_sm = 0;
 
@@ -768,29 +770,58 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     p.t_last = h->d_tlast.as<double>(); p.y_last = h->d_ylast.as<double>();
     p.queue = h->d_queue.as<unsigned long long>();
 
-    // launch geometry: one CTA per SM when the working set fills shared memory, more when it is small
+    // Register-resident kernel (cta2_core.cuh) for built-in problems with n_y <= 8 * 512: thread t owns C components.
     int optin = 0;
     CU_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    const int nvec = cta_num_vectors(a.method);
-    const size_t vec_bytes = (size_t)p.n_pad * 8;
-    size_t fit = ((size_t)optin - 1024) / vec_bytes;
     int smem_per_sm = 0;
     CU_TRY(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
-    // Measured (profiles/r01_notes.md, n_y = 4096): where the stage vectors live (shared memory vs the L2-resident
-    // slab) changes the kernel time by < 2 %, but TWO 512-thread CTAs per SM beat one 1024-thread CTA by 10 %
-    // (one CTA's barrier waits hide behind the other's arithmetic).  So: 512 threads, and only as many vectors in
-    // shared memory as still leave room for two CTAs per SM.
-    int block = N <= 256 ? 128 : N <= 1024 ? 256 : 512;
-    if (g_opt_cta_block > 0) block = g_opt_cta_block;
-    const size_t fit2 = ((size_t)smem_per_sm / 2 > 2048 + vec_bytes) ? ((size_t)smem_per_sm / 2 - 2048) / vec_bytes : 0;
-    p.n_smem_vec = (unsigned)std::min<size_t>({fit, fit2, (size_t)nvec});
-    if (g_opt_cta_smem_vecs >= 0) p.n_smem_vec = std::min<unsigned>((unsigned)std::min<size_t>(fit, (size_t)nvec), (unsigned)g_opt_cta_smem_vecs);
-    const size_t smem = (size_t)p.n_smem_vec * vec_bytes;
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)(2048 / block), ((size_t)smem_per_sm) / (smem + 2048)}));
-    int grid = (int)std::min<unsigned long long>((unsigned long long)device_sm_count(h->device) * per_sm, B);
-    const size_t n_glob = (size_t)nvec - p.n_smem_vec;
-    if (h->d_scratch.ensure((size_t)grid * (n_glob + 2) * vec_bytes)) return -1;
-    p.scratch = h->d_scratch.as<double>();
+    const bool use_cta2 = !user_rhs && g_opt_cta_kernel != 1 && N <= (size_t)8 * cta2_max_block;
+    int cta2_C = 0;
+    int block, grid;
+    size_t smem;
+    {
+        bool uni = true;
+        for (size_t i = 1; i < N && uni; i++) uni = (rt[i] == rt[0]) && (at[i] == at[0]);
+        p.uniform_tol = uni ? 1 : 0;
+        p.rtol0 = rt[0];
+        p.atol0 = at[0];
+    }
+    if (use_cta2) {
+        cta2_C = N <= (size_t)cta2_max_block ? 1 : N <= (size_t)2 * cta2_max_block ? 2 : N <= (size_t)4 * cta2_max_block ? 4 : 8;
+        block = (int)(((N + cta2_C - 1) / cta2_C + 31) / 32 * 32);
+        const size_t V = (size_t)block * cta2_C;
+        const int nkd = cta2_nkd(a.method);
+        smem = (size_t)(3 + cta2_nsm(nkd, cta2_C)) * V * 8;
+        if (smem + 1024 > (size_t)optin) { set_error("internal: CTA kernel shared-memory layout exceeds the device limit"); return -1; }
+        // registers: the kernel is compiled for <= 128 per thread (__launch_bounds__(512, 1))
+        const size_t by_regs = std::max<size_t>(1, (size_t)65536 / ((size_t)128 * block));
+        const size_t by_smem = std::max<size_t>(1, (size_t)smem_per_sm / (smem + 2048));
+        const int per_sm = (int)std::min<size_t>({(size_t)8, by_regs, by_smem});
+        grid = (int)std::min<unsigned long long>((unsigned long long)device_sm_count(h->device) * per_sm, B);
+        const size_t ngl = (size_t)std::max(1, cta2_ngl(nkd, cta2_C));
+        if (h->d_scratch.ensure((size_t)grid * ngl * V * 8)) return -1;
+        p.scratch = h->d_scratch.as<double>();
+    } else {
+        // launch geometry: one CTA per SM when the working set fills shared memory, more when it is small
+        const int nvec = cta_num_vectors(a.method);
+        const size_t vec_bytes = (size_t)p.n_pad * 8;
+        size_t fit = ((size_t)optin - 1024) / vec_bytes;
+        // Measured (profiles/r01_notes.md, n_y = 4096): where the stage vectors live (shared memory vs the L2-resident
+        // slab) changes the kernel time by < 2 %, but TWO 512-thread CTAs per SM beat one 1024-thread CTA by 10 %
+        // (one CTA's barrier waits hide behind the other's arithmetic).  So: 512 threads, and only as many vectors in
+        // shared memory as still leave room for two CTAs per SM.
+        block = N <= 256 ? 128 : N <= 1024 ? 256 : 512;
+        if (g_opt_cta_block > 0) block = g_opt_cta_block;
+        const size_t fit2 = ((size_t)smem_per_sm / 2 > 2048 + vec_bytes) ? ((size_t)smem_per_sm / 2 - 2048) / vec_bytes : 0;
+        p.n_smem_vec = (unsigned)std::min<size_t>({fit, fit2, (size_t)nvec});
+        if (g_opt_cta_smem_vecs >= 0) p.n_smem_vec = std::min<unsigned>((unsigned)std::min<size_t>(fit, (size_t)nvec), (unsigned)g_opt_cta_smem_vecs);
+        smem = (size_t)p.n_smem_vec * vec_bytes;
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)(2048 / block), ((size_t)smem_per_sm) / (smem + 2048)}));
+        grid = (int)std::min<unsigned long long>((unsigned long long)device_sm_count(h->device) * per_sm, B);
+        const size_t n_glob = (size_t)nvec - p.n_smem_vec;
+        if (h->d_scratch.ensure((size_t)grid * (n_glob + 2) * vec_bytes)) return -1;
+        p.scratch = h->d_scratch.as<double>();
+    }
 
     size_t row_cap = 0;
     if (want_rows) row_cap = a.n_t_eval ? a.n_t_eval : (a.expected_size ? a.expected_size : 64);
@@ -808,7 +839,11 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
                 return -1;
             }
         } else {
-            CU_TRY((fp == FP_STRICT ? cta_launch_strict : cta_launch_fast)(a.rhs_id, a.method, p, grid, block, smem, h->stream));
+            if (use_cta2) {
+                CU_TRY((fp == FP_STRICT ? cta2_launch_strict : cta2_launch_fast)(a.rhs_id, a.method, cta2_C, p, grid, block, smem, h->stream));
+            } else {
+                CU_TRY((fp == FP_STRICT ? cta_launch_strict : cta_launch_fast)(a.rhs_id, a.method, p, grid, block, smem, h->stream));
+            }
         }
         h->launches++;
         CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
@@ -952,6 +987,13 @@ __global__ void ensemble_final_kernel(const double* __restrict__ partial, int nb
 // ------------------------------------------------------------------------------------------------
 // FP64 throughput probe: 8 independent DFMA chains per thread
 // ------------------------------------------------------------------------------------------------
+// the production build's sin/cos (rk_core.cuh psin/pcos), one thread per element, for the accuracy test
+__global__ void sincos_probe_kernel(const double* __restrict__ x, double* __restrict__ s, double* __restrict__ c, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { s[i] = cyrk::fast::psin(x[i]); c[i] = cyrk::fast::pcos(x[i]); }
+}
+
 __global__ void fp64_probe_kernel(double* out, int iters, double a, double b)
 {
     double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -1230,8 +1272,26 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "root_batch")) { g_opt_root_batch = value; return 0; }
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
+    if (!strcmp(name, "cta_kernel")) { g_opt_cta_kernel = value; return 0; }
     set_error("unknown option '%s'", name);
     return -1;
+}
+
+int cyrk_b200_debug_sincos(const double* x, double* sin_out, double* cos_out, size_t n, int device)
+{
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_error("no CUDA device %d", device); return -1; }
+    double *dx = nullptr, *ds = nullptr, *dc = nullptr;
+    int rc = -1;
+    if (cudaMalloc(&dx, n * 8) == cudaSuccess && cudaMalloc(&ds, n * 8) == cudaSuccess && cudaMalloc(&dc, n * 8) == cudaSuccess &&
+        cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice) == cudaSuccess) {
+        sincos_probe_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dx, ds, dc, n);
+        if (cudaMemcpy(sin_out, ds, n * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
+            cudaMemcpy(cos_out, dc, n * 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+            rc = 0;
+    }
+    if (rc != 0) { set_error("debug_sincos: %s", cudaGetErrorString(cudaGetLastError())); }
+    cudaFree(dx); cudaFree(ds); cudaFree(dc);
+    return rc;
 }
 
 double cyrk_b200_measure_fp64_tflops(int device)

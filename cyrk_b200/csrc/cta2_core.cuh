@@ -1,0 +1,551 @@
+// cta2_core.cuh -- adaptive explicit Runge-Kutta solver for LARGE systems, one CTA per trajectory,
+// REGISTER-RESIDENT variant (n_y <= C * blockDim.x, C in {1,2,4,8}, i.e. up to 4096 components at 512 threads).
+//
+// The first CTA kernel (cta_core.cuh) keeps every working vector in shared memory / an L2 slab behind a run-time
+// address selection and brackets every loop with __syncthreads(); it measured 11.7 SM-cycles per component-attempt
+// on BASELINE config 4 (largey, n_y = 4096, RK45) against an FP64-pipe bound of ~4.5.  Here instead
+//   * thread t OWNS the components i = t + c*blockDim.x, c < C, for the whole trajectory: y_old and the most
+//     frequently read stage derivatives K_0..K_{NREG-1} of those components live in REGISTERS, the next NSM
+//     derivatives in shared memory, only the remainder (DOP853) in a per-CTA L2-resident slab -- all placements are
+//     compile-time, so every access is a plain register / LDS / LDG with a constant offset;
+//   * the only data other threads ever read is the stage INPUT vector (the right-hand side may couple components),
+//     which is double-buffered in shared memory: ONE __syncthreads() per right-hand-side evaluation, plus one for
+//     the (double-buffered) error-norm reduction -- 7 barriers per RK45 attempt instead of 16;
+//   * the problem's auxiliary table (largey: the per-component rates) sits in shared memory as well;
+//   * every step-size decision comes from a CTA-wide reduction, so all threads take the same branch;
+//   * accepted rows are streamed to HBM straight from the owning threads, one coalesced row per step.
+//
+// Reference behaviour restated: the same file:line map as rk_core.cuh / cta_core.cuh.  The production build uses the
+// thread path's controller arithmetic (reciprocal instead of division, squared norm, one-Newton-step root); the strict
+// build uses the reference formulas verbatim.  The error norm is summed by a tree (reference: sequential loop,
+// rk.cpp:1047-1072): an O(eps*sqrt(n_y)) difference, documented in DESIGN.md.
+//
+// Not available on this path (the host shim rejects them): extra outputs, events, stored dense output.
+#pragma once
+#include "rk_core.cuh"
+#include "cta_core_params.h"
+
+namespace cyrk {
+namespace CYRK_FP_NS {
+
+template <class Prob, int METHOD, int C>
+struct Cta2Solver {
+    using Tab = typename TabFor<METHOD>::type;
+    using Ld = TabLd<Tab>;
+    using LdDop = TabLd<TabDOP853>;
+    static constexpr int NS = Tab::NS;
+    static constexpr int NK = Tab::NK;
+    static constexpr int NKD = Tab::NK_DENSE;
+    static constexpr int QO = Tab::Q_ORDER;
+    // Placement of K_0 .. K_{NKD-1}.  Registers: y_old plus NREG derivative vectors within a budget of 40 doubles per
+    // thread.  Shared memory: two stage-input buffers, the aux table, then NSM derivative vectors -- sized for the
+    // largest block (512 threads): 227 KB / (C*512*8 B) slots.
+    static constexpr int NREG = cta2_nreg(NKD, C);
+    static constexpr int NSM = cta2_nsm(NKD, C);
+    static constexpr int NGL = cta2_ngl(NKD, C);
+    static_assert(NKD == cta2_nkd(METHOD), "cta_core_params.h out of sync with tableaux.cuh");
+
+    double yo[C];
+    double kr[NREG > 0 ? NREG : 1][C];
+    double* buf0; double* buf1;  // stage-input buffers (shared memory), V doubles each (no run-time indexed member arrays:
+                                 // they would drag the whole solver state into local memory)
+    double* ybuf;                // the buffer that holds y_now (last y_new computed, or y0)
+    double* aux;                 // [V] shared memory
+    double* ksm;                 // [NSM][V] shared memory
+    double* kgl;                 // [NGL][V] global slab
+    double (*red)[32];
+    int red_phase;
+    unsigned V, T, tid, n;
+    bool prepared;
+    const char* args;
+    double t_old, t_now, t_end, t_start, step, step_size, min_step, t_last, inv_n;
+    unsigned size, steps, nrej, nfev, te_old;
+    int status;
+    bool fwd, te_finished, error_flag;
+    bool uni_tol;
+    double rt0, at0;
+
+    CYRK_DI unsigned comp(int c) const { return tid + (unsigned)c * T; }
+    template <int J> CYRK_DI double kget(int c) const
+    {
+        if constexpr (J < NREG) return kr[J][c];
+        else if constexpr (J < NREG + NSM) return ksm[(unsigned)(J - NREG) * V + comp(c)];
+        else return kgl[(unsigned long long)(J - NREG - NSM) * V + comp(c)];
+    }
+    template <int J> CYRK_DI void kset(int c, double v)
+    {
+        if constexpr (J < NREG) kr[J][c] = v;
+        else if constexpr (J < NREG + NSM) ksm[(unsigned)(J - NREG) * V + comp(c)] = v;
+        else kgl[(unsigned long long)(J - NREG - NSM) * V + comp(c)] = v;
+    }
+    CYRK_DI double rtol_at(const CtaParams& p, unsigned i) const { return uni_tol ? rt0 : p.rtol[i]; }
+    CYRK_DI double atol_at(const CtaParams& p, unsigned i) const { return uni_tol ? at0 : p.atol[i]; }
+
+    // Sum over the CTA with ONE barrier: warp shuffles, one shared-memory hop into the phase's row, then every warp
+    // reduces the (<= 32) warp partials redundantly.  The next call uses the other row, and the barrier of this call
+    // orders it after every read of that row.  Summation order is fixed (tree), so results do not depend on timing.
+    CYRK_DI double cta_sum(double v)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const unsigned warp = tid >> 5, lane = tid & 31u, nwarp = (T + 31u) >> 5;
+        if (lane == 0) red[red_phase][warp] = v;
+        __syncthreads();
+        double w = lane < nwarp ? red[red_phase][lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        red_phase ^= 1;
+        return w;
+    }
+
+    template <class CoefFn, int NTERMS>
+    CYRK_DI double dot_k(int c, CoefFn) const
+    {
+        double acc = 0.0;
+        bool first = true;
+        static_for<0, NTERMS>([&](auto jj) {
+            constexpr int J = decltype(jj)::value;
+            constexpr double cf = CoefFn::get(J);
+            if constexpr (cf != 0.0) {
+                if (first) { acc = CoefFn::ld(J) * kget<J>(c); first = false; }
+                else       { acc += CoefFn::ld(J) * kget<J>(c); }
+            }
+        });
+        return acc;
+    }
+    template <int S> struct ARow { CYRK_HD static constexpr double get(int j) { return Tab::a(S, j); } CYRK_DI static double ld(int j) { return Ld::a(S, j); } };
+    struct BRow { CYRK_HD static constexpr double get(int j) { return Tab::b(j); } CYRK_DI static double ld(int j) { return Ld::b(j); } };
+    struct ERow { CYRK_HD static constexpr double get(int j) { return Tab::e(j); } CYRK_DI static double ld(int j) { return Ld::e(j); } };
+    struct E3Row { CYRK_HD static constexpr double get(int j) { return TabDOP853::e3(j); } CYRK_DI static double ld(int j) { return LdDop::e3(j); } };
+    struct E5Row { CYRK_HD static constexpr double get(int j) { return TabDOP853::e5(j); } CYRK_DI static double ld(int j) { return LdDop::e5(j); } };
+    template <int Q> struct PRow { CYRK_HD static constexpr double get(int j) { return Tab::p(Q, j); } CYRK_DI static double ld(int j) { return Ld::p(Q, j); } };
+    template <int R> struct XRow { CYRK_HD static constexpr double get(int j) { return TabDOP853::ax(R, j); } CYRK_DI static double ld(int j) { return LdDop::ax(R, j); } };
+    template <int R> struct DRow { CYRK_HD static constexpr double get(int j) { return TabDOP853::d(R, j); } CYRK_DI static double ld(int j) { return LdDop::d(R, j); } };
+
+    // One component of the right-hand side as a real function call: inlined, the functor would be replicated
+    // (stages + 1) * C times per attempt -- the first build of this kernel was 19 456 instructions (311 KB) for
+    // largey/RK45/C=8 and spent 30 % of its stall samples waiting for instruction fetch (profiles/r01_notes.md).
+    // Problems whose functor is a handful of instructions say so with `static constexpr bool INLINE_EVAL = true`.
+    static __device__ __noinline__ double eval_call(unsigned i, double t, const double* in, unsigned n, const char* args, const double* aux)
+    {
+        return Prob::eval(i, t, in, n, args, aux);
+    }
+    CYRK_DI static double eval_one(unsigned i, double t, const double* in, unsigned n, const char* args, const double* aux)
+    {
+        if constexpr (Prob::INLINE_EVAL) return Prob::eval(i, t, in, n, args, aux);
+        else return eval_call(i, t, in, n, args, aux);
+    }
+
+    // K_J = f(t, in) for the components this thread owns; `in` must be complete (the caller has synchronised)
+    template <int J>
+    CYRK_DI void eval_rhs(double t, const double* in)
+    {
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const unsigned i = comp(c);
+            kset<J>(c, i < n ? eval_one(i, t, in, n, args, aux) : 0.0);
+        }
+        nfev++;
+    }
+
+    // stages of one attempt (rk.cpp:695-776, 886-1025, 1154-1412); leaves y_new in `ybuf`
+    CYRK_DI void compute_stages()
+    {
+        // never start in the buffer that holds y_now (it is still read below); then alternate
+        double* in = (ybuf == buf0) ? buf1 : buf0;
+        double* other = (ybuf == buf0) ? buf0 : buf1;
+        {
+            const double a10 = Ld::a(1, 0);
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const double k0 = kget<0>(c);
+                if constexpr (Tab::STAGE1_STEP_FIRST) in[comp(c)] = yo[c] + (step * k0 * a10);
+                else                                  in[comp(c)] = yo[c] + step * (a10 * k0);
+            }
+            __syncthreads();
+            eval_rhs<1>(t_old + Ld::c(1) * step, in);
+            double* t = in; in = other; other = t;
+        }
+        static_for<2, NS>([&](auto ss) {
+            constexpr int S = decltype(ss)::value;
+#pragma unroll
+            for (int c = 0; c < C; c++) in[comp(c)] = yo[c] + (step * dot_k<ARow<S>, S>(c, ARow<S>{}));
+            __syncthreads();
+            eval_rhs<S>(t_old + Ld::c(S) * step, in);
+            double* t = in; in = other; other = t;
+        });
+#pragma unroll
+        for (int c = 0; c < C; c++) in[comp(c)] = yo[c] + (step * dot_k<BRow, NS>(c, BRow{}));
+        __syncthreads();
+        eval_rhs<NS>(t_now, in);
+        ybuf = in;
+    }
+
+    // rk.cpp:778-823, 1027-1075, 1414-1489.  Strict build: returns err (reference formulas).  Production build:
+    // returns err^2 (reciprocal + squared norm, like the thread path).
+    CYRK_DI double estimate_error(const CtaParams& p)
+    {
+        if constexpr (!Tab::IS_DOP) {
+            double part = 0.0;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const unsigned i = comp(c);
+                if (i < n) {
+                    const double e = dot_k<ERow, NK>(c, ERow{});
+                    const double yn = ybuf[i];
+#if CYRK_FP_STRICT
+                    const double sc = e / (atol_at(p, i) + fmax(fabs(yo[c]), fabs(yn)) * rtol_at(p, i));
+                    part += (sc * sc);
+#else
+                    const double sc = e * fast_rcp(fma(fabs(larger_mag(yo[c], yn)), rtol_at(p, i), atol_at(p, i)));
+                    part = fma(sc, sc, part);
+#endif
+                }
+            }
+            const double norm = cta_sum(part);
+#if CYRK_FP_STRICT
+            return step_size * sqrt(norm) / sqrt((double)n);
+#else
+            return (step_size * step_size) * norm * inv_n;
+#endif
+        } else {
+            double p3 = 0.0, p5 = 0.0;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const unsigned i = comp(c);
+                if (i < n) {
+                    const double yn = ybuf[i];
+#if CYRK_FP_STRICT
+                    const double scale_inv = 1.0 / (atol_at(p, i) + fmax(fabs(yo[c]), fabs(yn)) * rtol_at(p, i));
+#else
+                    const double scale_inv = fast_rcp(fma(fabs(larger_mag(yo[c], yn)), rtol_at(p, i), atol_at(p, i)));
+#endif
+                    const double e3 = scale_inv * dot_k<E3Row, NS>(c, E3Row{});
+                    const double e5 = scale_inv * dot_k<E5Row, NS>(c, E5Row{});
+                    p3 += (e3 * e3);
+                    p5 += (e5 * e5);
+                }
+            }
+            const double n3 = cta_sum(p3);
+            const double n5 = cta_sum(p5);
+            if ((n5 == 0.0) && (n3 == 0.0)) return 0.0;
+            const double denom = n5 + 0.01 * n3;
+#if CYRK_FP_STRICT
+            return step_size * n5 / sqrt(denom * (double)n);
+#else
+            return (step_size * step_size) * (n5 * n5) * inv_n / denom;
+#endif
+        }
+    }
+
+    // rk.cpp:183-282 (scalar part verbatim; runs once per trajectory)
+    CYRK_DI void first_step_size(const CtaParams& p)
+    {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const unsigned i = comp(c);
+            if (i < n) {
+                const double scale = atol_at(p, i) + fabs(yo[c]) * rtol_at(p, i);
+                const double a0 = yo[c] / scale;
+                const double a1 = kget<0>(c) / scale;
+                a += (a0 * a0);
+                b += (a1 * a1);
+            }
+        }
+        const double ny_sqrt = sqrt((double)n);
+        const double d0 = sqrt(cta_sum(a)) / ny_sqrt;
+        const double d1 = sqrt(cta_sum(b)) / ny_sqrt;
+        double h0 = 1.0e-6;
+        if (!((d0 < 1.0e-5) || (d1 < 1.0e-5))) h0 = 0.01 * d0 / d1;
+        const double h0_dir = fwd ? h0 : -h0;
+        t_now = t_old + h0_dir;
+        double* in = buf1;                        // buf0 keeps y0 == y_now
+#pragma unroll
+        for (int c = 0; c < C; c++) in[comp(c)] = yo[c] + h0_dir * kget<0>(c);
+        __syncthreads();
+        double cc = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const unsigned i = comp(c);
+            if (i < n) {
+                const double f1 = eval_one(i, t_now, in, n, args, aux);
+                const double scale = atol_at(p, i) + fabs(yo[c]) * rtol_at(p, i);
+                const double a2 = (f1 - kget<0>(c)) / scale;
+                cc += (a2 * a2);
+            }
+        }
+        nfev++;
+        const double d2 = sqrt(cta_sum(cc)) / (h0 * ny_sqrt);
+        double h1;
+        if ((d1 <= 1.0e-15) && (d2 <= 1.0e-15)) h1 = fmax(1.0e-6, h0 * 1.0e-3);
+        else h1 = pow((0.01 / fmax(d1, d2)), Tab::err_exponent());
+        step_size = fmax(min_step_at(t_old, fwd), fmin(100.0 * h0, h1));
+    }
+
+    // interpolated own component c at x = (t - t_old)/h for the step just taken (dense.cpp:71-170, rk.cpp set_Q_array)
+    CYRK_DI double interp_component(int c, double x, double h) const
+    {
+        if constexpr (!Tab::IS_DOP) {
+            double cp = x;
+            double acc = kget<0>(c) * cp;               // Q_0 = k_0
+            static_for<1, QO>([&](auto qq) {
+                constexpr int Q = decltype(qq)::value;
+                cp *= x;
+                acc += dot_k<PRow<Q>, NK>(c, PRow<Q>{}) * cp;
+            });
+            acc *= h;
+            return yo[c] + acc;
+        } else {
+            const double q0 = h * dot_k<DRow<3>, 16>(c, DRow<3>{});
+            const double q1 = h * dot_k<DRow<2>, 16>(c, DRow<2>{});
+            const double q2 = h * dot_k<DRow<1>, 16>(c, DRow<1>{});
+            const double q3 = h * dot_k<DRow<0>, 16>(c, DRow<0>{});
+            const double delta_y = ybuf[comp(c)] - yo[c];
+            const double sum_dy = kget<NS>(c) + kget<0>(c);
+            const double q4 = 2.0 * delta_y - h * sum_dy;
+            const double q5 = h * kget<0>(c) - delta_y;
+            const double q6 = delta_y;
+            double acc = q0;
+            acc *= x;
+            acc += q1; acc *= (1.0 - x);
+            acc += q2; acc *= x;
+            acc += q3; acc *= (1.0 - x);
+            acc += q4; acc *= x;
+            acc += q5; acc *= (1.0 - x);
+            acc += q6; acc *= x;
+            return yo[c] + acc;
+        }
+    }
+
+    // DOP853: the three extra stages of the 7th-order interpolant (rk.cpp:1491-1676).  Their inputs go through the
+    // stage buffer that does not hold y_now.
+    CYRK_DI void dense_extra_stages()
+    {
+        if constexpr (Tab::IS_DOP) {
+            double* in = (ybuf == buf0) ? buf1 : buf0;
+#pragma unroll
+            for (int c = 0; c < C; c++) in[comp(c)] = yo[c] + dot_k<XRow<0>, 13>(c, XRow<0>{}) * step;
+            __syncthreads();
+            eval_rhs<13>(t_old + (step * LdDop::cx(0)), in);
+            __syncthreads();                       // every thread is done reading `in` before it is rewritten
+#pragma unroll
+            for (int c = 0; c < C; c++) in[comp(c)] = yo[c] + dot_k<XRow<1>, 14>(c, XRow<1>{}) * step;
+            __syncthreads();
+            eval_rhs<14>(t_old + (step * LdDop::cx(1)), in);
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < C; c++) in[comp(c)] = yo[c] + dot_k<XRow<2>, 15>(c, XRow<2>{}) * step;
+            __syncthreads();
+            eval_rhs<15>(t_old + (step * LdDop::cx(2)), in);
+            __syncthreads();
+        }
+    }
+
+    CYRK_DI void save_row_from_ybuf(const CtaParams& p, unsigned long long traj, double t)
+    {
+        if (p.t_rows != nullptr && size < p.row_cap) {
+            const unsigned long long r = traj * p.row_cap + size;
+            if (tid == 0) p.t_rows[r] = t;
+            double* dst = p.y_rows + r * n;
+#pragma unroll
+            for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) dst[i] = ybuf[i]; }
+        }
+        t_last = t;
+        size++;
+    }
+
+    // whole trajectory (cysolver.cpp:303-543 setup, 752-1000 loop)
+    CYRK_DI void solve(const CtaParams& p, unsigned long long traj)
+    {
+        const double* ts = p.t_span + traj * p.t_span_stride;
+        t_start = ts[0]; t_end = ts[1];
+        fwd = (t_end - t_start) >= 0.0;
+        args = p.args + traj * p.args_stride;
+        size = steps = nrej = nfev = 0;
+        status = ST_NO_ERROR; error_flag = false; te_finished = false;
+        t_old = t_now = t_start; step = 0.0; step_size = 0.0;
+        t_last = d_nan();
+        inv_n = 1.0 / (double)n;
+        const double* y0 = p.y0 + traj * n;
+        ybuf = buf0;
+        __syncthreads();                                   // the previous trajectory's readers are done with the buffers
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const unsigned i = comp(c);
+            const double v = i < n ? y0[i] : 0.0;
+            yo[c] = v;
+            ybuf[i] = v;
+        }
+        Prob::prepare(args, n, aux, prepared && p.args_stride == 0);   // cooperative; ends with __syncthreads()
+        prepared = true;
+        __syncthreads();
+        eval_rhs<0>(t_now, ybuf);                          // RHS evaluation #1
+        if (p.n_t_eval == 0) save_row_from_ybuf(p, traj, t_now);
+        te_old = fwd ? 0u : p.n_t_eval;
+        bool bad_first = false;
+        if (p.first_step != 0.0) {
+            if (p.first_step < 0.0 || p.first_step > (fabs(t_end - t_start) * 0.5)) { status = ST_BAD_INITIAL_STEP_SIZE; bad_first = true; }
+            step_size = p.first_step;
+        } else {
+            first_step_size(p);
+        }
+        // ---- main loop: one reference take_step per iteration
+        while (!bad_first) {
+            if (status != ST_NO_ERROR || error_flag) break;
+            if (t_now == t_end) { t_old = t_end; status = ST_SUCCESSFUL_INTEGRATION; break; }
+            if (steps >= p.max_num_steps) {
+                error_flag = true;
+                status = p.user_max_steps ? ST_MAX_STEPS_USER_EXCEEDED : ST_MAX_STEPS_SYSARCH_EXCEEDED;
+                break;
+            }
+            min_step = min_step_at(t_old, fwd);
+            if (step_size < min_step) step_size = min_step;
+            else if (p.max_step < step_size) step_size = p.max_step;
+            bool rejected = false;
+            for (;;) {                              // rk.cpp:447-523
+                if (!(step_size >= min_step)) { status = ST_STEP_SIZE_ERROR_SPACING; break; }
+                double over;
+                if (fwd) { step = step_size;  t_now = t_old + step; over = t_now - t_end; }
+                else     { step = -step_size; t_now = t_old + step; over = t_end - t_now; }
+                if (over > 0.0) {
+                    t_now = t_end;
+                    step = t_now - t_old;
+                    step_size = fwd ? step : -step;
+                }
+                compute_stages();
+                const double err = estimate_error(p);
+#if CYRK_FP_STRICT
+                const double err_safe = 0.9 / pow(err, Tab::err_exponent());
+                if (err < 1.0) {
+                    double f = 10.0;
+                    if (err != 0.0) f = fmin(f, err_safe);
+                    if (rejected) f = fmin(f, 1.0);
+                    step_size *= f;
+                    break;
+                }
+                step_size *= fmax(0.2, err_safe);
+#else
+                // err holds err^2 here (see estimate_error); same decisions, no pow()/sqrt()
+                const double err_safe = safe_factor<Tab::METHOD - METHOD_RK23, 1>(err);
+                if (err < 1.0) {
+                    double f = fmin(10.0, err_safe);
+                    if (rejected) f = fmin(f, 1.0);
+                    step_size *= f;
+                    break;
+                }
+                step_size *= (err_safe > 0.2) ? err_safe : 0.2;
+#endif
+                rejected = true;
+                nrej++;
+            }
+            steps++;
+            // ---- t_eval emission (cysolver.cpp:838-967) or plain save (:968-972)
+            bool do_save = true;
+            if (p.n_t_eval > 0 && !te_finished) {
+                do_save = false;
+                unsigned lo = 0, hi = p.n_t_eval;
+                while (lo < hi) { const unsigned m = (lo + hi) >> 1; if (p.t_eval[m] < t_now) lo = m + 1; else hi = m; }
+                unsigned up = lo;
+                while (up < p.n_t_eval && !(t_now < p.t_eval[up])) up++;
+                unsigned idx_new;
+                if (lo == up) idx_new = lo;
+                else if (fwd) { idx_new = up; if (idx_new == p.n_t_eval) te_finished = true; }
+                else          { idx_new = lo; if (idx_new == 0) te_finished = true; }
+                const bool any = fwd ? (idx_new > te_old) : (te_old > idx_new);
+                const unsigned delta = fwd ? (idx_new - te_old) : (te_old - idx_new);
+                if (any) {
+                    const double h = t_now - t_old;
+                    dense_extra_stages();
+                    for (unsigned q = 0; q < delta; q++) {
+                        const double ti = fwd ? p.t_eval[te_old + q] : p.t_eval[te_old - q - 1];
+                        const double x = (ti - t_old) / h;
+                        const bool row = (p.t_rows != nullptr && size < p.row_cap);
+                        const bool last = (q + 1 == delta);
+                        if (row || last) {
+                            const unsigned long long r = traj * p.row_cap + size;
+                            if (row && tid == 0) p.t_rows[r] = ti;
+#pragma unroll
+                            for (int c = 0; c < C; c++) {
+                                const unsigned i = comp(c);
+                                if (i < n) {
+                                    const double v = interp_component(c, x, h);     // interpolate straight into the output row
+                                    if (row) p.y_rows[r * n + i] = v;
+                                    if (last) p.y_last[traj * n + i] = v;
+                                }
+                            }
+                        }
+                        t_last = ti;
+                        size++;
+                    }
+                }
+                te_old = idx_new;
+            }
+            if (do_save && !error_flag) save_row_from_ybuf(p, traj, t_now);
+            // roll: y_old <- y_now, K_0 <- K_NS (FSAL); own components only, no barrier needed
+            t_old = t_now;
+#pragma unroll
+            for (int c = 0; c < C; c++) { yo[c] = ybuf[comp(c)]; kset<0>(c, kget<NS>(c)); }
+        }
+        // ---- results
+        if (p.n_t_eval == 0) {
+            double* yl = p.y_last + traj * n;
+#pragma unroll
+            for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) yl[i] = ybuf[i]; }
+        } else if (size == 0) {
+            double* yl = p.y_last + traj * n;
+#pragma unroll
+            for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) yl[i] = t_last; }   // NaN
+        }
+        if (tid == 0) {
+            p.status[traj] = status;
+            p.size[traj] = size;
+            p.steps_taken[traj] = steps;
+            p.n_rejected[traj] = nrej;
+            p.nfev[traj] = nfev;
+            p.t_last[traj] = t_last;
+        }
+    }
+};
+
+template <class Prob, int METHOD, int C>
+CYRK_DI void rk_cta2_body(const CtaParams& p)
+{
+    using Solver = Cta2Solver<Prob, METHOD, C>;
+    extern __shared__ double smem[];
+    __shared__ double red[2][32];
+    __shared__ unsigned long long next_traj;
+    Solver S;
+    S.n = p.n;
+    S.T = blockDim.x;
+    S.tid = threadIdx.x;
+    S.V = blockDim.x * (unsigned)C;
+    S.red = red;
+    S.red_phase = 0;
+    S.prepared = false;
+    S.buf0 = smem;
+    S.buf1 = smem + S.V;
+    S.aux = smem + 2u * S.V;
+    S.ksm = smem + 3u * S.V;
+    S.kgl = p.scratch + (unsigned long long)blockIdx.x * (unsigned long long)(Solver::NGL > 0 ? Solver::NGL : 1) * S.V;
+    S.uni_tol = p.uniform_tol != 0;
+    S.rt0 = p.rtol0;
+    S.at0 = p.atol0;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) next_traj = atomicAdd(p.queue, 1ULL);
+        __syncthreads();
+        const unsigned long long traj = next_traj;
+        if (traj >= p.n_traj) break;
+        S.solve(p, traj);
+    }
+}
+
+template <class Prob, int METHOD, int C>
+__global__ void __launch_bounds__(cta2_max_block, 1) rk_cta2_kernel(const __grid_constant__ CtaParams p)
+{
+    rk_cta2_body<Prob, METHOD, C>(p);
+}
+
+}  // namespace CYRK_FP_NS
+}  // namespace cyrk

@@ -14,6 +14,8 @@ struct CtaParams {
     unsigned      t_span_stride;
     const double* rtol;          // [n]  (floored at 100 eps on the host)
     const double* atol;          // [n]
+    int    uniform_tol;          // every component has the same tolerances (rtol0, atol0): no array reads
+    double rtol0, atol0;
     double max_step, first_step;
     unsigned max_num_steps;
     int    user_max_steps;
@@ -33,5 +35,18 @@ struct CtaParams {
     unsigned  n_smem_vec;        // how many of the working vectors live in shared memory
     unsigned long long* queue;
 };
+
+// ---- register-resident kernel (cta2_core.cuh): compile-time placement of the stage derivatives K_0..K_{nkd-1}
+// for C components per thread.  Shared by the kernel and the host launcher.
+constexpr int cta2_max_block = 512;
+constexpr int cta2_reg_doubles(int C) { return C >= 8 ? 32 : 40; }            // y_old + NREG derivative vectors per thread
+constexpr int cta2_nkd(int method) { return method == 3 ? 4 : method == 4 ? 7 : 16; }      // RK23 / RK45 / DOP853 (+3 dense)
+constexpr int cta2_nreg(int nkd, int C) { return (cta2_reg_doubles(C) / C - 1) < nkd ? (cta2_reg_doubles(C) / C - 1) : nkd; }
+constexpr int cta2_sm_slots(int C) { return (227 * 1024 - 1024) / (C * cta2_max_block * 8); }
+constexpr int cta2_nsm(int nkd, int C)
+{
+    return (nkd - cta2_nreg(nkd, C)) < (cta2_sm_slots(C) - 3) ? (nkd - cta2_nreg(nkd, C)) : (cta2_sm_slots(C) - 3);
+}
+constexpr int cta2_ngl(int nkd, int C) { return nkd - cta2_nreg(nkd, C) - cta2_nsm(nkd, C); }
 
 }  // namespace cyrk

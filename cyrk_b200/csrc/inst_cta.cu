@@ -1,6 +1,7 @@
 // inst_cta.cu -- instantiates the CTA-per-trajectory kernels (both large built-in problems, three methods) for
 // ONE floating-point mode: compiled twice by the Makefile (-DCYRK_FP_NS=fast -fmad=true / strict -fmad=false).
 #include "cta_core.cuh"
+#include "cta2_core.cuh"
 #include "problems_large.cuh"
 #include "problems_builtin.cuh"
 #include "cta_solver.h"
@@ -29,6 +30,36 @@ cudaError_t by_method(int method, const CtaParams& p, int grid, int block, size_
     default: return cudaErrorInvalidValue;
     }
 }
+// register-resident kernels (cta2_core.cuh): C components per thread
+template <class Prob, int METHOD, int C>
+cudaError_t go2(const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(rk_cta2_kernel<Prob, METHOD, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rk_cta2_kernel<Prob, METHOD, C><<<grid, block, smem, s>>>(p);
+    return cudaGetLastError();
+}
+template <class Prob, int METHOD>
+cudaError_t by_c(int C, const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
+{
+    switch (C) {
+    case 1: return go2<Prob, METHOD, 1>(p, grid, block, smem, s);
+    case 2: return go2<Prob, METHOD, 2>(p, grid, block, smem, s);
+    case 4: return go2<Prob, METHOD, 4>(p, grid, block, smem, s);
+    case 8: return go2<Prob, METHOD, 8>(p, grid, block, smem, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+template <class Prob>
+cudaError_t by_method2(int method, int C, const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
+{
+    switch (method) {
+    case METHOD_RK23: return by_c<Prob, METHOD_RK23>(C, p, grid, block, smem, s);
+    case METHOD_RK45: return by_c<Prob, METHOD_RK45>(C, p, grid, block, smem, s);
+    case METHOD_DOP853: return by_c<Prob, METHOD_DOP853>(C, p, grid, block, smem, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
 }  // namespace
 }  // namespace CYRK_FP_NS
 
@@ -36,6 +67,13 @@ cudaError_t CYRK_CAT2(cta_launch_, CYRK_FP_NS)(int rhs_id, int method, const Cta
 {
     if (rhs_id == RHS_LARGEY) return CYRK_FP_NS::by_method<ProbLargeY>(method, p, grid, block, smem, s);
     if (rhs_id == RHS_LARGEY_SIMPLE) return CYRK_FP_NS::by_method<ProbLargeYSimple>(method, p, grid, block, smem, s);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t CYRK_CAT2(cta2_launch_, CYRK_FP_NS)(int rhs_id, int method, int C, const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
+{
+    if (rhs_id == RHS_LARGEY) return CYRK_FP_NS::by_method2<ProbLargeY>(method, C, p, grid, block, smem, s);
+    if (rhs_id == RHS_LARGEY_SIMPLE) return CYRK_FP_NS::by_method2<ProbLargeYSimple>(method, C, p, grid, block, smem, s);
     return cudaErrorInvalidValue;
 }
 

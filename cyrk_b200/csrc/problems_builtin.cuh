@@ -80,8 +80,8 @@ struct ProbAccuracy {           // cysolver_test.pyx:32-39
     __device__ __forceinline__ static void rhs(double* dy, double t, const double* y, const char*)
     {
         const double y0 = y[0], y1 = y[1];
-        dy[0] = sin(t) - y1;
-        dy[1] = cos(t) + y0;
+        dy[0] = CYRK_FP_NS::psin(t) - y1;
+        dy[1] = CYRK_FP_NS::pcos(t) + y0;
     }
 };
 
@@ -161,9 +161,9 @@ struct ProbPendulum {           // cysolver_test.pyx:122-141, Performance/pendul
         const double coeff_1 = (-3. * g / (2. * l));
         const double coeff_2 = (3. / (m * (l * l)));
         const double y0 = y[0], y1 = y[1];
-        const double torque = 0.1 * sin(t);
+        const double torque = 0.1 * CYRK_FP_NS::psin(t);
         dy[0] = y1;
-        dy[1] = coeff_1 * sin(y0) + coeff_2 * torque;
+        dy[1] = coeff_1 * CYRK_FP_NS::psin(y0) + coeff_2 * torque;
     }
 };
 
@@ -177,13 +177,13 @@ struct ProbArbitraryArgs {      // cysolver_test.pyx:144-178: heterogeneous stru
         const double coeff_1 = (-3. * g / (2. * l));
         const double coeff_2 = (3. / (m * (l * l)));
         const double y0 = y[0], y1 = y[1];
-        const double torque = 0.1 * sin(t);
+        const double torque = 0.1 * CYRK_FP_NS::psin(t);
         if (p->cause_fail) {
             dy[0] = pow(100 * t, 1000.0);
             dy[1] = pow(-100 * t, 1000.0);
         } else {
             dy[0] = y1;
-            dy[1] = coeff_1 * sin(y0) + coeff_2 * torque;
+            dy[1] = coeff_1 * CYRK_FP_NS::psin(y0) + coeff_2 * torque;
         }
     }
 };
@@ -194,7 +194,7 @@ struct ProbPendulumPreEval {    // cysolver_test.pyx:182-222: the pre-eval hook 
     {
         const double* p = reinterpret_cast<const double*>(args);
         const double l = p[0], m = p[1], g = p[2];
-        out[0] = 0.1 * sin(t);
+        out[0] = 0.1 * CYRK_FP_NS::psin(t);
         out[1] = (-3. * g / (2. * l));
         out[2] = (3. / (m * (l * l)));
     }
@@ -204,7 +204,7 @@ struct ProbPendulumPreEval {    // cysolver_test.pyx:182-222: the pre-eval hook 
         pre_eval(s, t, y, args);
         const double y0 = y[0], y1 = y[1];
         dy[0] = y1;
-        dy[1] = s[1] * sin(y0) + s[2] * s[0];
+        dy[1] = s[1] * CYRK_FP_NS::psin(y0) + s[2] * s[0];
     }
 };
 
@@ -217,9 +217,9 @@ struct ProbPendulumDrag {       // Documentation/Advanced_CySolver.md:127-152; a
         const double coeff_1 = (-3. * g / (2. * l));
         const double coeff_2 = (3. / (m * (l * l)));
         const double y0 = y[0], y1 = y[1];
-        const double torque = 0.1 * sin(t);
+        const double torque = 0.1 * CYRK_FP_NS::psin(t);
         dy[0] = y1;
-        double d1 = coeff_1 * sin(y0) + coeff_2 * torque;
+        double d1 = coeff_1 * CYRK_FP_NS::psin(y0) + coeff_2 * torque;
         d1 -= c * y1;
         dy[1] = d1;
         dy[2] = torque;

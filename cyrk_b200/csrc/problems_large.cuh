@@ -6,7 +6,11 @@
 
 namespace cyrk {
 
+#ifndef CYRK_LARGEY_INLINE
+#define CYRK_LARGEY_INLINE false
+#endif
 struct ProbLargeY {
+    static constexpr bool INLINE_EVAL = CYRK_LARGEY_INLINE;     // register-resident CTA kernel: call vs inline the functor
     // r_i = r * 0.9999^(i+1) by SEQUENTIAL multiplication like the reference loop (one thread; shared args are
     // prepared once per CTA), so the rates are bit-identical to the reference's.
     __device__ __forceinline__ static void prepare(const char* args, unsigned n, double* aux, bool reuse)
@@ -20,17 +24,25 @@ struct ProbLargeY {
     __device__ __forceinline__ static double eval(unsigned i, double t, const double* y, unsigned n, const char*, const double* aux)
     {
         const double pi = 3.14159265358979323846;
-        if (i < (n - 1)) return aux[i] * y[i] * sin(2 * pi * t / 5.0 + y[i + 1] / 50.0);
-        return aux[i] * y[i] * sin(2 * pi * t / 5.0);
+#if CYRK_FP_STRICT
+        if (i < (n - 1)) return aux[i] * y[i] * CYRK_FP_NS::psin(2 * pi * t / 5.0 + y[i + 1] / 50.0);
+        return aux[i] * y[i] * CYRK_FP_NS::psin(2 * pi * t / 5.0);
+#else
+        // production build: the two divisions by constants become multiplications (<= 1 ulp each, like the FMA contraction)
+        const double ph = (2 * pi * t) * 0.2;
+        const double x = (i < (n - 1)) ? fma(y[i + 1], 0.02, ph) : ph;
+        return aux[i] * y[i] * CYRK_FP_NS::psin(x);
+#endif
     }
 };
 
 struct ProbLargeYSimple {
+    static constexpr bool INLINE_EVAL = true;
     __device__ __forceinline__ static void prepare(const char*, unsigned, double*, bool) { __syncthreads(); }
     __device__ __forceinline__ static double eval(unsigned i, double t, const double*, unsigned, const char*, const double*)
     {
         const double pi = 3.14159265358979323846;
-        return i == 0 ? sin(2.0 * pi * t / 10.0) : 0.0;
+        return i == 0 ? CYRK_FP_NS::psin(2.0 * pi * t / 10.0) : 0.0;
     }
 };
 

@@ -212,6 +212,9 @@ size_t   cyrk_b200_get_d2h_bytes(void* h);
 int      cyrk_b200_set_option(const char* name, int value);
 /* FP64 FMA throughput probe (dependent-free DFMA streams on every SM): returns TFLOP/s. */
 double   cyrk_b200_measure_fp64_tflops(int device);
+/* Diagnostic: the production build's sin/cos for the built-in right-hand sides, evaluated on the device for n host
+ * values (accuracy test against libm).  Returns 0 / -1. */
+int      cyrk_b200_debug_sincos(const double* x, double* sin_out, double* cos_out, size_t n, int device);
 
 #pragma GCC visibility pop
 

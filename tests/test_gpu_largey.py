@@ -74,3 +74,58 @@ def test_largey_simple_and_unsupported_features():
         c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, args=[-0.5, float(n)], dense_output=True)
     with pytest.raises(c.CyrkB200Error):
         c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, args=[-0.5, float(n)], events=[c.Event("y0")])
+
+
+@pytest.mark.parametrize("n", [700, 1500, 3000, 5000])
+def test_register_resident_kernel_sizes(oracle, n):
+    """n_y = 700 / 1500 / 3000 exercise C = 2 / 4 / 8 components per thread with a ragged last block of components
+    (cta2_core.cuh); n_y = 5000 is past its limit and runs on the shared-memory/slab kernel (cta_core.cuh)."""
+    rng = np.random.default_rng(11)
+    B = 3
+    y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (B, n)))
+    args = [-0.5, float(n)]
+    te = np.linspace(0, 10, 5)
+    for method, t_eval in (("RK45", None), ("RK23", te), ("DOP853", te)):
+        r = c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method=method, args=args, rtol=1e-6, atol=1e-8, t_eval=t_eval)
+        ref = oracle.solve("largey", (0.0, 10.0), y0[1], method, 1e-6, 1e-8, args=args, t_eval=t_eval)
+        v = r[1]
+        assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken), (method, n)
+        assert int(r.nfev[1]) == ref.nfev
+        assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
+        assert np.all(np.abs(v.y - ref.y) <= _tol(ref.y, 1e-6, 1e-8))
+
+
+def test_both_cta_kernels_agree():
+    """The register-resident kernel and the shared-memory/slab kernel are two schedules of the same arithmetic:
+    same step counts, states equal to rounding (the error-norm partial sums are grouped differently)."""
+    rng = np.random.default_rng(12)
+    n, B = 1024, 4
+    y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (B, n)))
+    out = []
+    for kernel in (0, 1):
+        c.lib().cyrk_b200_set_option(b"cta_kernel", kernel)
+        try:
+            out.append(c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method="RK45", args=[-0.5, float(n)], rtol=1e-6, atol=1e-8))
+        finally:
+            c.lib().cyrk_b200_set_option(b"cta_kernel", 0)
+    a, b = out
+    assert np.array_equal(a.steps_taken, b.steps_taken) and np.array_equal(a.n_rejected, b.n_rejected)
+    assert np.allclose(a.y_last, b.y_last, rtol=1e-9, atol=1e-12)
+
+
+def test_cta_per_component_tolerances():
+    """Non-uniform rtol/atol arrays take the array path of the register-resident kernel."""
+    rng = np.random.default_rng(13)
+    n, B = 600, 2
+    y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (B, n)))
+    rt = np.full(n, 1e-6); rt[::2] = 1e-7
+    at = np.full(n, 1e-8)
+    outs = []
+    for kernel in (0, 1):
+        c.lib().cyrk_b200_set_option(b"cta_kernel", kernel)
+        try:
+            outs.append(c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method="RK45", args=[-0.5, float(n)], rtol=rt, atol=at))
+        finally:
+            c.lib().cyrk_b200_set_option(b"cta_kernel", 0)
+    assert np.array_equal(outs[0].steps_taken, outs[1].steps_taken)
+    assert np.allclose(outs[0].y_last, outs[1].y_last, rtol=1e-9, atol=1e-12)
