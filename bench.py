@@ -64,12 +64,23 @@ WORKLOADS = {
                    kwargs=dict(num_extra=1, store="final", events="c3"),
                    descr="C3: damped pendulum RK23 rtol=1e-6 atol=1e-8, 1 extra output, events theta=0 / omega=0 (dir -1) / "
                          "terminal t = t_stop(traj) ~ U(2,12), store=final + event lists"),
+    # configs[3]: CTA-per-trajectory path.  F_rhs per COMPONENT: largey 6 + 1 sin (counted as 1), largey_simple ~0.
+    "C4": dict(rhs="largey", method="RK45", ny=4096, f_rhs=7 * 4096, rtol=1e-6, atol=1e-8, batch=4096,
+               kwargs=dict(store="rows", expected_size=40),
+               descr="C4: largey (n_y=4096) RK45 rtol=1e-6 atol=1e-8, 4096 trajectories, every accepted row stored (4 GB)"),
+    "C4simple": dict(rhs="largey_simple", method="RK45", ny=4096, f_rhs=0, rtol=1e-6, atol=1e-8, batch=4096,
+                     kwargs=dict(store="rows", expected_size=40),
+                     descr="C4 memory-side demonstrator: largey_simple (n_y=4096, RHS ~ free) RK45, 4096 trajectories, rows stored"),
 }
 
 
 def make_inputs(w, n, seed):
     """Synthetic inputs of SURVEY.md 8d (numpy default_rng / PCG64)."""
     rng = np.random.default_rng(seed)
+    if w["rhs"] in ("largey", "largey_simple"):
+        y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (n, w["ny"])))
+        args = np.array([-0.5, float(w["ny"])])
+        return np.ascontiguousarray(y0), args
     if w["rhs"] == "lotkavolterra":
         y0 = np.stack([rng.uniform(5, 15, n), rng.uniform(2.5, 7.5, n)], 1)
         args = np.array([1.5, 1.0, 3.0, 1.0])
@@ -152,9 +163,9 @@ def cpu_reference_run(w, n, threads=None, seed=12345):
 def run_reference_arm(a, w, rank, world):
     if rank != 0:
         return
-    n = 65536
+    n = 65536 if w["ny"] <= 32 else 512
     for _ in range(a.warmup):
-        cpu_reference_run(w, 4096)
+        cpu_reference_run(w, 4096 if w["ny"] <= 32 else 64)
     secs, kind, threads = 0.0, "port", 1
     for _ in range(a.steps):
         r = cpu_reference_run(w, n)
@@ -283,6 +294,8 @@ def main():
         ker_ms_per_launch = ker_ms / a.steps
         achieved_tf = alg_flops_per_launch / (ker_ms_per_launch * 1e-3) / 1e12
         io_bytes = B * (w["ny"] * 8 + 5 * 4 + 8 + w["ny"] * 8)      # y0 in; counters, t_last, y_last out
+        if w.get("kwargs", {}).get("store") == "rows" and "t_eval" not in w.get("kwargs", {}):
+            io_bytes += (steps_acc + B) * (w["ny"] + 1) * 8           # every accepted row (t, y) of this rank
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -312,9 +325,10 @@ def main():
         }
         if world == 1 and not a.no_cpu_baseline:
             # bounded sample: calibrate on 4096 trajectories, then aim for ~10 s of CPU work
-            cal = cpu_reference_run(w, 4096)
-            rate = 4096 / max(cal["seconds"], 1e-6)
-            n = int(min(max(rate * 10.0, 8192), 1 << 21))
+            n_cal = 4096 if w["ny"] <= 32 else 64
+            cal = cpu_reference_run(w, n_cal)
+            rate = n_cal / max(cal["seconds"], 1e-6)
+            n = int(min(max(rate * 10.0, 2 * n_cal), 1 << 21))
             r = cpu_reference_run(w, n)
             line["cpu_baseline"] = {"value": r["n"] / r["seconds"], "unit": "solves/s", "cores": r["threads"],
                                     "kind": r["kind"],

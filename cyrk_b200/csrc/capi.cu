@@ -775,7 +775,7 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     CU_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     int smem_per_sm = 0;
     CU_TRY(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
-    const bool use_cta2 = !user_rhs && g_opt_cta_kernel != 1 && N <= (size_t)8 * cta2_max_block;
+    const bool use_cta2 = g_opt_cta_kernel != 1 && N <= (size_t)8 * cta2_max_block;
     int cta2_C = 0;
     int block, grid;
     size_t smem;
@@ -833,7 +833,7 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         CU_TRY(cudaMemsetAsync(h->d_queue.p, 0, 8, h->stream));
         CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
         if (user_rhs) {
-            if (user_rhs_launch_cta(a.rhs_id, a.method, fp == FP_STRICT, h->device, p, grid, block, smem, h->stream) != cudaSuccess) {
+            if (user_rhs_launch_cta(a.rhs_id, a.method, use_cta2 ? cta2_C : 0, fp == FP_STRICT, h->device, p, grid, block, smem, h->stream) != cudaSuccess) {
                 cudaGetLastError();
                 if (g_last_error.empty()) set_error("user CTA kernel launch failed");
                 return -1;

@@ -109,12 +109,13 @@ def test_large_user_rhs_compiles_on_cpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("method", ["RK23", "RK45", "DOP853"])
-def test_large_user_rhs_matches_oracle(oracle, method):
-    """A user-supplied large system (discrete diffusion chain, n_y = 96) through NVRTC on the CTA path vs the CPU
-    oracle driven with the same right-hand side as a ctypes callback."""
+@pytest.mark.parametrize("method,n", [("RK23", 96), ("RK45", 96), ("DOP853", 96), ("RK45", 700), ("DOP853", 1100)])
+def test_large_user_rhs_matches_oracle(oracle, method, n):
+    """A user-supplied large system (discrete diffusion chain; n_y = 96 / 700 / 1100 -> 1 / 2 / 4 components per
+    thread of the register-resident CTA kernel) through NVRTC vs the CPU oracle driven with the same right-hand side
+    as a ctypes callback."""
     import ctypes as C
-    n, B = 96, 3
+    B = 3
     u = c.UserRHS(CHAIN_SRC, "chain", n_y=0, args_bytes=8)
     rng = np.random.default_rng(9)
     y0 = rng.uniform(0.0, 1.0, (B, n))
