@@ -328,7 +328,7 @@ def main():
             n_cal = 4096 if w["ny"] <= 32 else 64
             cal = cpu_reference_run(w, n_cal)
             rate = n_cal / max(cal["seconds"], 1e-6)
-            n = int(min(max(rate * 10.0, 2 * n_cal), 1 << 21))
+            n = int(min(max(rate * 10.0, 2 * n_cal), (1 << 21) if w["ny"] <= 32 else 8192))   # (large n_y: bound the host copy of y0)
             r = cpu_reference_run(w, n)
             line["cpu_baseline"] = {"value": r["n"] / r["seconds"], "unit": "solves/s", "cores": r["threads"],
                                     "kind": r["kind"],
