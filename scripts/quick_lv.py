@@ -1,3 +1,4 @@
+"""C5 kernel timing sweep: refill_min x block (prep kernel on), 8 Mi Lotka-Volterra trajectories by default."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -7,7 +8,8 @@ B = int(os.environ.get('QB', 1 << 20))
 import torch
 y0 = torch.from_numpy(np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)).cuda()
 args_d = torch.tensor([1.5, 1, 3, 1], dtype=torch.float64, device='cuda'); ts_d = torch.tensor([0., 10.], dtype=torch.float64, device='cuda')
-for prep, refill, block in ((1, 1, 128), (1, 1, 64)):
+cfgs = [(1, 1, 128)] if not os.environ.get("SWEEP") else [(1, r, b) for r in (1, 2, 3, 4, 6) for b in (128, 256)]
+for prep, refill, block in cfgs:
     c.lib().cyrk_b200_set_option(b'block', block)
     c.lib().cyrk_b200_set_option(b"refill_min", refill)
     try: c.lib().cyrk_b200_set_option(b"prep", prep)
