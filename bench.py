@@ -212,6 +212,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION (this image's default): keep stdout to the
+        # one JSON line the contract asks for
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 

@@ -129,3 +129,22 @@ def test_cta_per_component_tolerances():
             c.lib().cyrk_b200_set_option(b"cta_kernel", 0)
     assert np.array_equal(outs[0].steps_taken, outs[1].steps_taken)
     assert np.allclose(outs[0].y_last, outs[1].y_last, rtol=1e-9, atol=1e-12)
+
+
+def test_cta_results_are_bitwise_reproducible():
+    """The register-resident kernel synchronises with one barrier per evaluation and double-buffered shared memory;
+    a missing barrier would show up as run-to-run differences.  Same batch three times (more trajectories than CTAs,
+    so trajectories land on different CTAs in different orders): bitwise identical rows."""
+    rng = np.random.default_rng(21)
+    n, B = 4096, 400
+    y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (B, n)))
+    ref = None
+    for rep in range(3):
+        r = c.cysolve_ivp_batch("largey", (0.0, 3.0), y0, method="RK45", args=[-0.5, float(n)], rtol=1e-6, atol=1e-8,
+                                t_eval=np.linspace(0.0, 3.0, 4))
+        cur = (np.array(r.steps_taken), np.array(r.n_rejected), np.array(r.y_last), np.array(r[B - 1].y), np.array(r[0].y))
+        if ref is None:
+            ref = cur
+        else:
+            assert all(np.array_equal(a, b) for a, b in zip(ref, cur))
+        r.close()
