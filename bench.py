@@ -38,8 +38,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # DRAM traffic per launch of the dominant kernel from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum),
-# same workload/batch as the bench line: profiles/r01_ncu_c5_lv_rk45_final.txt (468.3 MB read + 390.1 MB written).
-NCU_TRAFFIC_BYTES = {"C5": 858.4e6}
+# same workload/batch as the bench line: profiles/r01_ncu_c5_lv_rk45_final2.txt (454.3 MB read + 377.6 MB written;
+# algorithmic: y0 16 B + start-up record 40 B in, 44 B out per trajectory = 839 MB).
+NCU_TRAFFIC_BYTES = {"C5": 831.9e6}
 
 # F_attempt(m) = n_y*c_m + E_m*F_rhs + s   
 C_M = {"RK23": 25, "RK45": 62, "DOP853": 167}
@@ -211,6 +212,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    numa_cores = None
+    if world > 1:
+        # one process per GPU: keep this rank (and, by first touch, its pinned host buffers) on the GPU's NUMA node
+        from cyrk_b200.sharding import bind_to_device_numa
+        numa_cores = bind_to_device_numa(local_rank)
     if world > 1:
         # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION (this image's default): keep stdout to the
         # one JSON line the contract asks for
@@ -312,7 +318,9 @@ def main():
             "config": {"workload": w["descr"], "trajectories_per_gpu": B, "t_span": [0.0, 10.0],
                        "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (io_bytes / 1e6),
                        "rk_attempts_per_step": attempts_all, "rk_steps_per_s": steps_all * a.steps / (dev_ms * 1e-3) / a.steps,
-                       "all_success": bool(ok_all), "wall_ms_per_step": wall_ms / a.steps},
+                       "all_success": bool(ok_all), "wall_ms_per_step": wall_ms / a.steps,
+                       "host_binding": ("rank pinned to its GPU's NUMA-local cores (%d on rank 0)" % len(numa_cores)) if numa_cores
+                                       else "none"},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_wall_ms / a.steps},
             "gpu_launches": launches_all,
@@ -320,7 +328,7 @@ def main():
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak and fp64_peak > 0 else None,
                          "traffic": NCU_TRAFFIC_BYTES.get(a.workload) if B == WORKLOADS[a.workload]["batch"] else None,
-                         "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_c5_lv_rk45_final.txt)",
+                         "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_c5_lv_rk45_final2.txt)",
                          "peak_source": "in-run dependent-free DFMA probe (cyrk_b200_measure_fp64_tflops); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "flop_per_attempt": f_attempt, "kernel_ms_per_launch": ker_ms_per_launch,

@@ -85,7 +85,7 @@ void registry_init()
 // 8 Mi).  Below that the extra launch costs more than it saves and inline set-up with refill_min 4 is best.
 static int g_opt_refill_min = 0;      // 0 = automatic (1 with prep, 4 without)
 static int g_opt_prep = -1;           // -1 = automatic (n_traj >= 2 Mi), 1 = always, 0 = never
-static int g_opt_block = 128;
+static int g_opt_block = 0;            // threads per CTA of the thread-per-trajectory kernels; 0 = pick by occupancy (128 or 96)
 static int g_opt_cta_smem_vecs = -1;  // CTA path: working vectors kept in shared memory (-1 = as many as fit)
 static int g_opt_cta_block = 0;       // CTA path: threads per CTA (0 = by n_y)
 static int g_opt_cta_kernel = 0;      // CTA path: 0 = register-resident kernel where it applies, 1 = always the shared-memory/slab kernel
@@ -339,7 +339,7 @@ static int device_sm_count(int dev)
 //   copy-in stream  ->  two alternating compute streams  ->  copy-out stream
 // so PCIe traffic hides behind the solve kernels, and the tail of one chunk's persistent kernel overlaps the head of the
 // next (they run on different streams).  Results are identical to the single-launch path: trajectories are independent.
-static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* pe, BatchParams p, int grid, bool use_prep)
+static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* pe, BatchParams p, int grid, int block, bool use_prep)
 {
     const size_t B = a.n_traj, NY = pe->ny, NDY = pe->ny + pe->nextra;
     const size_t args_stride = (size_t)pe->nargs_dbl * sizeof(double);
@@ -409,7 +409,7 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
         q.status = p.status + off; q.size = p.size + off; q.steps_taken = p.steps_taken + off;
         q.n_rejected = p.n_rejected + off; q.nfev = p.nfev + off; q.t_last = p.t_last + off; q.y_last = p.y_last + off * NDY;
         q.queue = h->d_queue.as<unsigned long long>() + c;
-        const int cgrid = (int)std::min<unsigned long long>((unsigned long long)grid, (n + g_opt_block - 1) / g_opt_block);
+        const int cgrid = (int)std::min<unsigned long long>((unsigned long long)grid, (n + block - 1) / block);
         CU_TRY(cudaStreamWaitEvent(sc, e_in, 0));
         CU_TRY(cudaEventRecord(e_k0, sc));
         if (use_prep) {
@@ -419,7 +419,7 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
             q.prep = pr;
             h->launches++;
         }
-        if (pe->launch(a.method, VAR_LEAN, q, cgrid, g_opt_block, sc) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("solve kernel launch failed"); return -1; }
+        if (pe->launch(a.method, VAR_LEAN, q, cgrid, block, sc) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("solve kernel launch failed"); return -1; }
         h->launches++;
         CU_TRY(cudaEventRecord(e_k1, sc));
         // ---- copy out
@@ -503,25 +503,33 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     p.y_last = h->d_ylast.as<double>();
     p.queue = h->d_queue.as<unsigned long long>();
 
-    int grid = 0;
+    // CTA size: 128 threads unless 96 keeps more warps resident (register-heavy variants: Lorenz/DOP853 with rows + dense
+    // needs 186 registers -> 2 x 128 or 3 x 96 threads per SM; measured 5.31 vs 4.92 ms on the C2 t_eval+dense workload,
+    // while 64-thread CTAs, although they fit 10 warps, were no faster than 128).
+    int grid = 0, block = g_opt_block > 0 ? g_opt_block : 128;
     {
-        int ctas = g_opt_ctas_per_sm;
-        if (ctas <= 0) {
-            if (pe->occupancy(a.method, variant, &ctas, g_opt_block) != cudaSuccess) {
-                if (g_last_error.empty()) set_error("occupancy query failed for %s", pe->name(a.method, variant));
-                cudaGetLastError();
-                return -1;
-            }
-            if (ctas <= 0) { set_error("kernel %s cannot be resident with %d threads per CTA", pe->name(a.method, variant), g_opt_block); return -1; }
+        int ctas = 0;
+        if (pe->occupancy(a.method, variant, &ctas, block) != cudaSuccess) {
+            if (g_last_error.empty()) set_error("occupancy query failed for %s", pe->name(a.method, variant));
+            cudaGetLastError();
+            return -1;
         }
+        if (g_opt_block <= 0) {
+            int ctas96 = 0;
+            if (pe->occupancy(a.method, variant, &ctas96, 96) == cudaSuccess && ctas96 * 96 > ctas * 128) { block = 96; ctas = ctas96; }
+            else cudaGetLastError();
+        }
+        if (g_opt_ctas_per_sm > 0) ctas = g_opt_ctas_per_sm;
+        if (ctas <= 0) { set_error("kernel %s cannot be resident with %d threads per CTA", pe->name(a.method, variant), block); return -1; }
         grid = device_sm_count(h->device) * ctas;
-        const unsigned long long need = (B + g_opt_block - 1) / g_opt_block;
+        const unsigned long long need = (B + block - 1) / block;
         if ((unsigned long long)grid > need) grid = (int)std::max<unsigned long long>(need, 1);
+        if (getenv("CYRK_B200_DEBUG")) fprintf(stderr, "[cyrk_b200] %s: block %d, %d CTAs/SM, grid %d\n", pe->name(a.method, variant), block, ctas, grid);
     }
 
     // ---- host buffers + final-state variant + a batch worth cutting up: pipelined copy/compute path
     if (!device_io && variant == VAR_LEAN && B >= (size_t(1) << 21))
-        return solve_lean_pipelined(h, a, pe, p, grid, use_prep);
+        return solve_lean_pipelined(h, a, pe, p, grid, block, use_prep);
 
     // ---- inputs
     const size_t args_stride = (size_t)pe->nargs_dbl * sizeof(double);
@@ -635,7 +643,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             h->launches++;
             p.prep = h->d_prep.as<double>();
         }
-        if (pe->launch(a.method, variant, p, grid, g_opt_block, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("solve kernel launch failed"); return -1; }
+        if (pe->launch(a.method, variant, p, grid, block, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("solve kernel launch failed"); return -1; }
         h->launches++;
         CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
 
@@ -1266,7 +1274,7 @@ int cyrk_b200_set_option(const char* name, int value)
 {
     if (!name) return -1;
     if (!strcmp(name, "refill_min")) { g_opt_refill_min = value; return 0; }
-    if (!strcmp(name, "block")) { if (value < 32 || value > 1024 || value % 32) { set_error("block must be a multiple of 32 in [32,1024]"); return -1; } g_opt_block = value; return 0; }
+    if (!strcmp(name, "block")) { if (value == 0) { g_opt_block = 0; return 0; } if (value < 32 || value > 1024 || value % 32) { set_error("block must be a multiple of 32 in [32,1024]"); return -1; } g_opt_block = value; return 0; }
     if (!strcmp(name, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }
     if (!strcmp(name, "prep")) { g_opt_prep = value; return 0; }
     if (!strcmp(name, "root_batch")) { g_opt_root_batch = value; return 0; }

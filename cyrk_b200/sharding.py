@@ -5,7 +5,7 @@ or for the optional ensemble reduction (sum y, sum y^2, count -> one all-reduce 
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+from typing import Callable, List, Optional, Tuple
 
 import numpy as np
 
@@ -128,3 +128,27 @@ def solve_on_devices(diffeq, t_span, y0, devices, args=None, **kw):
         if e is not None:
             raise e
     return out
+
+
+def bind_to_device_numa(device: int) -> Optional[List[int]]:
+    """Pin the calling process to the CPU cores NVML reports as local to `device` (its PCIe root / NUMA node).
+
+    One process per GPU moves its shard through pinned host memory; with first-touch page placement the pinned buffers
+    then live on the GPU's own NUMA node, so the H2D / D2H copies of eight ranks do not cross the socket interconnect.
+    Call it BEFORE allocating pinned memory.  Returns the core list, or None when NVML / the topology is unavailable
+    (the process is then left as it was)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None

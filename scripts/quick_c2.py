@@ -12,7 +12,7 @@ for wl in ("C2full", "C3full"):
     common = dict(method=w["method"], rtol=w["rtol"], atol=w["atol"], store="final"); common.update(w.get("kwargs", {}))
     if common.get("events") == "c3":
         common["events"] = [c.Event("y0"), c.Event("y1", direction=-1), c.Event("t_minus_arg4", terminal=True)]
-    for block in (128, 96, 64, 32):
+    for block in (0, 128, 96):
         c.lib().cyrk_b200_set_option(b"block", block)
         res = None; best = 1e9
         for rep in range(4):
