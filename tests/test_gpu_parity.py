@@ -347,3 +347,71 @@ def test_device_ensemble_sums_match_numpy_and_are_deterministic():
     assert np.allclose(s1, r.y_last[ok].sum(0), rtol=1e-12) and np.allclose(s2, (r.y_last[ok] ** 2).sum(0), rtol=1e-12)
     t1, t2, m = r.ensemble_sums()
     assert np.array_equal(s1, t1) and np.array_equal(s2, t2) and m == n      # fixed summation order
+
+
+def test_full_size_c2_properties():
+    """BASELINE config 2's feature mix (Lorenz DOP853 rtol 1e-9, t_eval + dense_output, parameter sweep) at the largest
+    batch whose outputs stay small enough to check on the host (32 Ki x 250 samples): properties that do not need a
+    per-trajectory oracle."""
+    rng = np.random.default_rng(1)
+    B = 32 * 1024
+    args = np.stack([np.full(B, 10.0), rng.uniform(20, 35, B), np.full(B, 8 / 3)], 1)
+    y0 = np.tile([1.0, 0.0, 0.0], (B, 1))
+    te = np.linspace(0.0, 10.0, 250)
+    kw = dict(method="DOP853", args=args, rtol=1e-9, atol=1e-11, t_eval=te, dense_output=True, expected_size=448)
+    r = c.cysolve_ivp_batch("lorenz", (0.0, 10.0), y0, **kw)
+    assert (r.status == 1).all() and (r.size == te.size).all()
+    rows = np.array(r.y_rows)                                  # (B, 250, 3)
+    assert np.isfinite(rows).all() and np.array_equal(rows[:, 0, :], y0)      # the sample at t0 is y0 exactly
+    # the last sample is t_end: it must equal the final state the solver reports
+    assert np.array_equal(rows[:, -1, :], np.array(r.y_last))
+    # the stored interpolants evaluated at the t_eval times reproduce the emitted rows (same polynomial, same step);
+    # samples that coincide with a step end may come from the neighbouring interpolant: equal to rounding
+    out, codes = r.call(te[1:-1])
+    assert (codes == 0).all()
+    assert np.allclose(out, rows[:, 1:-1, :], rtol=1e-10, atol=1e-9)
+    # documented step statistics of the workload (SURVEY 8d probe: mean 258, 189-360 accepted; ~51 rejected)
+    assert 230 < r.steps_taken.mean() < 290 and r.steps_taken.min() > 150 and r.steps_taken.max() < 420
+    assert 30 < np.mean(r.n_rejected) < 80
+    # determinism
+    r2 = c.cysolve_ivp_batch("lorenz", (0.0, 10.0), y0, **kw)
+    assert np.array_equal(np.array(r2.y_rows), rows) and np.array_equal(r2.steps_taken, r.steps_taken)
+    # Lorenz trajectories stay on the attractor's bounded set
+    assert np.abs(rows).max() < 100.0
+
+
+def test_full_size_c3_properties():
+    """BASELINE config 3's feature mix at 1 Mi initial conditions (damped pendulum RK23, extra output, three events of
+    which one terminal at a per-trajectory time): structural properties of the event records."""
+    rng = np.random.default_rng(2)
+    B = 1 << 20
+    y0 = np.stack([rng.uniform(-1.5, 1.5, B), rng.uniform(-1, 1, B)], 1)
+    t_stop = rng.uniform(2.0, 12.0, B)
+    args = np.stack([np.ones(B), np.ones(B), np.full(B, 9.81), np.full(B, 1.5), t_stop], 1)
+    ev = [c.Event("y0"), c.Event("y1", direction=-1), c.Event("t_minus_arg4", terminal=True)]
+    r = c.cysolve_ivp_batch("pendulum_drag", (0.0, 10.0), y0, method="RK23", args=args, rtol=1e-6, atol=1e-8,
+                            events=ev, num_extra=1, store="final")
+    stopped = t_stop < 10.0
+    assert np.array_equal(r.status == 2, stopped) and np.array_equal(r.status == 1, ~stopped)
+    # a terminated trajectory ends exactly at its stop time (Brent on g = t - t_stop converges to the root itself)
+    assert np.allclose(np.array(r.t_last)[stopped], t_stop[stopped], rtol=0, atol=1e-9)
+    assert np.all(np.array(r.t_last)[~stopped] == 10.0)
+    # extra output = torque 0.1 sin(t) at the final time; state stays bounded (the pendulum is damped)
+    yl = np.array(r.y_last)
+    assert np.allclose(yl[:, 2], 0.1 * np.sin(np.array(r.t_last)), rtol=0, atol=1e-12)
+    assert np.abs(yl[:, 0]).max() < 1.6 and np.abs(yl[:, 1]).max() < 6.0
+    # event records of a sample of trajectories: roots ordered, theta ~ 0 at E0 roots, omega ~ 0 at E1 roots
+    for i in range(0, B, B // 64):
+        v = r[i]
+        t0, t1, t2 = v.t_events
+        assert np.all(np.diff(t0) > 0) and np.all(np.diff(t1) > 0)
+        if t0.size:
+            assert np.abs(v.y_events[0][0]).max() < 1e-6
+        if t1.size:
+            assert np.abs(v.y_events[1][1]).max() < 1e-6
+        assert (t2.size == 1) == bool(stopped[i])
+        if t2.size:
+            assert v.event_terminated and v.event_terminate_index == 2 and abs(t2[0] - t_stop[i]) < 1e-9
+    # step statistics: SURVEY 8d probe (undamped) mean 1480; the damped variant needs fewer
+    full = ~stopped
+    assert 500 < r.steps_taken[full].mean() < 1800
