@@ -154,7 +154,7 @@ struct Handle {
     size_t n_traj = 0, ny = 0, nx = 0, ndy = 0, q_order = 0;
     size_t n_events = 0, n_t_eval = 0;
     size_t row_cap = 0, dense_cap = 0, ev_cap = 0;
-    bool dense_output = false, device_io = false, solved = false;
+    bool dense_output = false, device_io = false, solved = false, cta_path = false;
     size_t args_stride = 0;
     // device arena
     DevBuf d_y0, d_args, d_tspan, d_teval, d_queue;
@@ -709,13 +709,14 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     const bool want_rows = a.store_mode == CYRK_STORE_ROWS;
     if (a.num_extra != 0) { set_error("the CTA-per-trajectory path does not capture extra outputs yet"); return -1; }
     if (a.n_events != 0) { set_error("the CTA-per-trajectory path does not support events yet"); return -1; }
-    if (a.dense_output) { set_error("the CTA-per-trajectory path does not store dense output yet (use t_eval)"); return -1; }
+    const bool dense = a.dense_output != 0;
     const bool user_rhs = a.rhs_id >= CYRK_RHS_USER_BASE;
     if (!user_rhs && (a.n_args == 0 || a.args_len < 8)) { set_error("largey problems need args = (decay_rate, ...)"); return -1; }
     if (N > 0x7fffffffu) { set_error("n_y too large"); return -1; }
     h->ny = N; h->nx = 0; h->ndy = N; h->q_order = 0;
     h->n_traj = B; h->n_events = 0; h->n_t_eval = a.n_t_eval;
-    h->dense_output = false; h->device_io = device_io;
+    h->dense_output = dense; h->device_io = device_io; h->cta_path = true;
+    h->q_order = a.method == CYRK_METHOD_RK23 ? 3 : a.method == CYRK_METHOD_RK45 ? 4 : 7;
     h->h2d_bytes = h->d2h_bytes = 0; h->launches = 0; h->kernel_ms = 0.f;
 
     CtaParams p;
@@ -794,6 +795,10 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         p.rtol0 = rt[0];
         p.atol0 = at[0];
     }
+    if (dense && !use_cta2) {
+        set_error("stored dense output on the CTA-per-trajectory path needs the register-resident kernel (n_y <= %d); use t_eval", 8 * cta2_max_block);
+        return -1;
+    }
     if (use_cta2) {
         cta2_C = N <= (size_t)cta2_max_block ? 1 : N <= (size_t)2 * cta2_max_block ? 2 : N <= (size_t)4 * cta2_max_block ? 4 : 8;
         block = (int)(((N + cta2_C - 1) / cta2_C + 31) / 32 * 32);
@@ -831,12 +836,22 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         p.scratch = h->d_scratch.as<double>();
     }
 
-    size_t row_cap = 0;
+    size_t row_cap = 0, dense_cap = 0;
     if (want_rows) row_cap = a.n_t_eval ? a.n_t_eval : (a.expected_size ? a.expected_size : 64);
+    if (dense) dense_cap = a.expected_size ? a.expected_size : 64;
     for (int pass = 0; pass < 2; pass++) {
         if (want_rows) {
             if (h->d_trows.ensure(B * row_cap * 8) || h->d_yrows.ensure(B * row_cap * N * 8)) return -1;
             p.t_rows = h->d_trows.as<double>(); p.y_rows = h->d_yrows.as<double>(); p.row_cap = (unsigned)row_cap;
+        }
+        if (dense) {
+            // one record per accepted step: [y_old | Q] = n_y * (Q_ORDER + 1) doubles (n_y = 4096, RK45: 164 KB)
+            if (h->d_dense_t.ensure(B * dense_cap * 8) || h->d_dense_state.ensure(B * dense_cap * N * (h->q_order + 1) * 8) ||
+                h->d_dense_count.ensure(B * 4) || h->h_dense_count.ensure(B * 4))
+                return -1;
+            p.dense_output = 1;
+            p.dense_t = h->d_dense_t.as<double>(); p.dense_state = h->d_dense_state.as<double>();
+            p.dense_count = h->d_dense_count.as<unsigned>(); p.dense_cap = (unsigned)dense_cap;
         }
         CU_TRY(cudaMemsetAsync(h->d_queue.p, 0, 8, h->stream));
         CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
@@ -856,17 +871,19 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         h->launches++;
         CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
         if ((want_rows || !device_io) && download(h, h->h_size, h->d_size, B * 4)) return -1;
+        if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
         CU_TRY(cudaStreamSynchronize(h->stream));
         { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; }
-        if (!want_rows) break;
-        size_t mx = 0;
-        const unsigned* sz = h->h_size.as<unsigned>();
-        for (size_t i = 0; i < B; i++) mx = std::max<size_t>(mx, sz[i]);
-        if (mx <= row_cap) break;
+        if (!want_rows && !dense) break;
+        size_t mx = 0, mxd = 0;
+        if (want_rows) { const unsigned* sz = h->h_size.as<unsigned>(); for (size_t i = 0; i < B; i++) mx = std::max<size_t>(mx, sz[i]); }
+        if (dense) { const unsigned* dc = h->h_dense_count.as<unsigned>(); for (size_t i = 0; i < B; i++) mxd = std::max<size_t>(mxd, dc[i]); }
+        if (mx <= row_cap && mxd <= dense_cap) break;
         if (pass == 1) { set_error("internal: arena overflow after the exact-capacity re-run"); return -1; }
-        row_cap = mx;
+        row_cap = std::max(row_cap, mx);
+        dense_cap = std::max(dense_cap, mxd);
     }
-    h->row_cap = row_cap; h->dense_cap = 0; h->ev_cap = 0;
+    h->row_cap = row_cap; h->dense_cap = dense_cap; h->ev_cap = 0;
     if (!device_io) {
         if (download(h, h->h_status, h->d_status, B * 4) || download(h, h->h_steps, h->d_steps, B * 4) ||
             download(h, h->h_nrej, h->d_nrej, B * 4) || download(h, h->h_nfev, h->d_nfev, B * 4) ||
@@ -919,7 +936,7 @@ static int solve_impl(Handle* h, const SolveArgs& a)
     if (h->bind(a.device)) return -1;
     registry_init();
     const int fp = (a.flags & CYRK_FLAG_STRICT_FP) ? FP_STRICT : FP_FAST;
-    h->rhs_id = a.rhs_id; h->method = a.method; h->fp_mode = fp;
+    h->rhs_id = a.rhs_id; h->method = a.method; h->fp_mode = fp; h->cta_path = false;
 
     if (a.rhs_id == CYRK_RHS_LARGEY || a.rhs_id == CYRK_RHS_LARGEY_SIMPLE) {
         if (solve_cta_path(h, a, fp)) return -1;
@@ -1201,6 +1218,37 @@ int cyrk_b200_call_vectorize(void* hv, const double* t, size_t n_t, double* out,
         for (size_t i = 0; i < B; i++) st[i] = (st[i] == 1 || st[i] == 2) ? ST_DENSE_OUTPUT_NOT_SAVED : ST_INTEGRATION_NOT_SUCCESSFUL;
         if (h->device_io) { CU_TRY(cudaMemcpy(codes, st.data(), B * 4, cudaMemcpyHostToDevice)); }
         else memcpy(codes, st.data(), B * 4);
+        return 0;
+    }
+    if (h->cta_path) {
+        // CTA-path solution: coefficient-major records, one CTA per (trajectory, query time)
+        CtaDenseEvalParams q;
+        memset(&q, 0, sizeof(q));
+        q.n_traj = B; q.n = (unsigned)h->ny; q.n_query = (unsigned)n_t;
+        if (h->d_q_t.ensure(n_t * 8) || h->d_q_code.ensure(B * 4)) return -1;
+        CU_TRY(cudaMemcpyAsync(h->d_q_t.p, t, n_t * 8, h->device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        q.t_query = h->d_q_t.as<double>();
+        q.t_span = h->in_tspan; q.t_span_stride = (unsigned)h->tspan_stride;
+        q.status = h->d_status.as<int>();
+        q.dense_t = h->d_dense_t.as<double>(); q.dense_state = h->d_dense_state.as<double>();
+        q.dense_count = h->d_dense_count.as<unsigned>(); q.dense_cap = (unsigned)h->dense_cap;
+        double* d_out = out;
+        if (!h->device_io) {
+            if (h->d_q_out.ensure(B * n_t * NDY * 8)) return -1;
+            d_out = h->d_q_out.as<double>();
+        }
+        q.out = d_out;
+        q.code = h->device_io ? codes : h->d_q_code.as<int>();
+        CU_TRY(cudaMemsetAsync(q.code, 0, B * 4, h->stream));
+        const unsigned long long pairs = (unsigned long long)B * n_t;
+        if (pairs > 0x7fffffffull) { set_error("too many query points"); return -1; }
+        const int blk = h->ny >= 256 ? 256 : 64;
+        CU_TRY((h->fp_mode == FP_STRICT ? cta_dense_eval_strict : cta_dense_eval_fast)(h->method, q, (int)pairs, blk, h->stream));
+        if (!h->device_io) {
+            CU_TRY(cudaMemcpyAsync(out, d_out, B * n_t * NDY * 8, cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaMemcpyAsync(codes, q.code, B * 4, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CU_TRY(cudaStreamSynchronize(h->stream));
         return 0;
     }
     Dispatch disp;

@@ -20,7 +20,8 @@
 // build uses the reference formulas verbatim.  The error norm is summed by a tree (reference: sequential loop,
 // rk.cpp:1047-1072): an O(eps*sqrt(n_y)) difference, documented in DESIGN.md.
 //
-// Not available on this path (the host shim rejects them): extra outputs, events, stored dense output.
+// Stored dense output: one coalesced record [y_old | Q_0 | .. | Q_{QO-1}] per accepted step, evaluated afterwards by
+// cta_dense_eval_kernel.  Not available on this path (the host shim rejects them): extra outputs, events.
 #pragma once
 #include "rk_core.cuh"
 #include "cta_core_params.h"
@@ -59,7 +60,7 @@ struct Cta2Solver {
     bool prepared;
     const char* args;
     double t_old, t_now, t_end, t_start, step, step_size, min_step, t_last, inv_n;
-    unsigned size, steps, nrej, nfev, te_old;
+    unsigned size, steps, nrej, nfev, te_old, n_dense;
     int status;
     bool fwd, te_finished, error_flag;
     bool uni_tol;
@@ -355,6 +356,49 @@ struct Cta2Solver {
         size++;
     }
 
+    // One interpolant record (dense.cpp:27-37, rk.cpp set_Q_array: 825-862, 1077-1131, 1491-1676) for the step just
+    // taken; `degenerate` = interpolant #0 at t0, whose K is still all zero.  DOP853: the caller
+    // has run dense_extra_stages().
+    CYRK_DI void store_dense(const CtaParams& p, unsigned long long traj, bool degenerate)
+    {
+        if (n_dense < p.dense_cap) {
+            const unsigned long long r = traj * p.dense_cap + n_dense;
+            if (tid == 0) p.dense_t[r] = t_now;
+            double* rec = p.dense_state + r * (unsigned long long)n * (QO + 1);
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const unsigned i = comp(c);
+                if (i < n) {
+                    rec[i] = yo[c];
+                    double q[QO];
+                    if (degenerate) {
+#pragma unroll
+                        for (int k = 0; k < QO; k++) q[k] = 0.0;
+                    } else if constexpr (!Tab::IS_DOP) {
+                        q[0] = kget<0>(c);
+                        static_for<1, QO>([&](auto qq) {
+                            constexpr int Q = decltype(qq)::value;
+                            q[Q] = dot_k<PRow<Q>, NK>(c, PRow<Q>{});
+                        });
+                    } else {
+                        q[0] = step * dot_k<DRow<3>, 16>(c, DRow<3>{});
+                        q[1] = step * dot_k<DRow<2>, 16>(c, DRow<2>{});
+                        q[2] = step * dot_k<DRow<1>, 16>(c, DRow<1>{});
+                        q[3] = step * dot_k<DRow<0>, 16>(c, DRow<0>{});
+                        const double delta_y = ybuf[i] - yo[c];
+                        const double sum_dy = kget<NS>(c) + kget<0>(c);
+                        q[4] = 2.0 * delta_y - step * sum_dy;
+                        q[5] = step * kget<0>(c) - delta_y;
+                        q[6] = delta_y;
+                    }
+#pragma unroll
+                    for (int k = 0; k < QO; k++) rec[(unsigned long long)n * (1 + k) + i] = q[k];
+                }
+            }
+        }
+        n_dense++;
+    }
+
     // whole trajectory (cysolver.cpp:303-543 setup, 752-1000 loop)
     CYRK_DI void solve(const CtaParams& p, unsigned long long traj)
     {
@@ -362,7 +406,7 @@ struct Cta2Solver {
         t_start = ts[0]; t_end = ts[1];
         fwd = (t_end - t_start) >= 0.0;
         args = p.args + traj * p.args_stride;
-        size = steps = nrej = nfev = 0;
+        size = steps = nrej = nfev = n_dense = 0;
         status = ST_NO_ERROR; error_flag = false; te_finished = false;
         t_old = t_now = t_start; step = 0.0; step_size = 0.0;
         t_last = d_nan();
@@ -383,6 +427,11 @@ struct Cta2Solver {
         eval_rhs<0>(t_now, ybuf);                          // RHS evaluation #1
         if (p.n_t_eval == 0) save_row_from_ybuf(p, traj, t_now);
         te_old = fwd ? 0u : p.n_t_eval;
+        if (p.dense_output) {
+            // interpolant #0 at t0: Q == 0 (quirk 9); DOP853 spends its three extra evaluations on it in the reference
+            store_dense(p, traj, true);
+            if constexpr (Tab::IS_DOP) nfev += 3;
+        }
         bool bad_first = false;
         if (p.first_step != 0.0) {
             if (p.first_step < 0.0 || p.first_step > (fabs(t_end - t_start) * 0.5)) { status = ST_BAD_INITIAL_STEP_SIZE; bad_first = true; }
@@ -440,6 +489,12 @@ struct Cta2Solver {
                 nrej++;
             }
             steps++;
+            bool extra_done = false;
+            if (p.dense_output) {                          // cysolver.cpp:785-806
+                dense_extra_stages();
+                extra_done = true;
+                store_dense(p, traj, false);
+            }
             // ---- t_eval emission (cysolver.cpp:838-967) or plain save (:968-972)
             bool do_save = true;
             if (p.n_t_eval > 0 && !te_finished) {
@@ -456,7 +511,7 @@ struct Cta2Solver {
                 const unsigned delta = fwd ? (idx_new - te_old) : (te_old - idx_new);
                 if (any) {
                     const double h = t_now - t_old;
-                    dense_extra_stages();
+                    if (!extra_done) dense_extra_stages();
                     for (unsigned q = 0; q < delta; q++) {
                         const double ti = fwd ? p.t_eval[te_old + q] : p.t_eval[te_old - q - 1];
                         const double x = (ti - t_old) / h;
@@ -504,6 +559,7 @@ struct Cta2Solver {
             p.n_rejected[traj] = nrej;
             p.nfev[traj] = nfev;
             p.t_last[traj] = t_last;
+            if (p.dense_count != nullptr) p.dense_count[traj] = n_dense;
         }
     }
 };
@@ -545,6 +601,85 @@ template <class Prob, int METHOD, int C>
 __global__ void __launch_bounds__(cta2_max_block, 1) rk_cta2_kernel(const __grid_constant__ CtaParams p)
 {
     rk_cta2_body<Prob, METHOD, C>(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Post-hoc dense evaluation for CTA-path solutions: one CTA per (trajectory, query time); semantics of
+// CySolverResult::call / call_vectorize (cy/cysolution.cpp:511-616) and CySolverDense::call (cy/dense.cpp:71-170),
+// the same lookup rules as dense_eval_body in rk_core.cuh.
+// ------------------------------------------------------------------------------------------------
+template <int METHOD>
+CYRK_DI void cta_dense_eval_body(const CtaDenseEvalParams& p)
+{
+    using Tab = typename TabFor<METHOD>::type;
+    constexpr int QO = Tab::Q_ORDER;
+    const unsigned long long pair = blockIdx.x;
+    const unsigned long long traj = pair / p.n_query;
+    const unsigned q = (unsigned)(pair - traj * p.n_query);
+    const int st = p.status[traj];
+    int code = ST_NO_ERROR;
+    const unsigned nrec = p.dense_count[traj] < p.dense_cap ? p.dense_count[traj] : p.dense_cap;
+    const double* ts = p.t_span + traj * p.t_span_stride;
+    const double t = p.t_query[q];
+    if (!(st == ST_SUCCESSFUL_INTEGRATION || st == ST_EVENT_TERMINATED)) code = ST_INTEGRATION_NOT_SUCCESSFUL;
+    else if (nrec == 0) code = ST_DENSE_OUTPUT_NOT_SAVED;
+    else if ((t < fmin(ts[0], ts[1])) || (t > fmax(ts[0], ts[1]))) code = ST_ARGUMENT_ERROR;
+    if (code != ST_NO_ERROR) {                       // uniform over the CTA
+        if (threadIdx.x == 0) atomicCAS(p.code + traj, 0, code);
+        return;
+    }
+    const double* times = p.dense_t + traj * p.dense_cap;
+    const bool fwd = (ts[1] - ts[0]) >= 0.0;
+    unsigned idx = 0;
+    if (nrec > 1) {
+        unsigned lo = 0, hi = nrec;
+        if (fwd) {
+            while (lo < hi) { const unsigned m = (lo + hi) >> 1; if (!(t < times[m])) lo = m + 1; else hi = m; }
+            idx = lo;
+        } else {
+            while (lo < hi) { const unsigned m = (lo + hi) >> 1; if (times[nrec - 1 - m] < t) lo = m + 1; else hi = m; }
+            idx = nrec - lo - 1;
+        }
+    }
+    if (idx >= nrec) idx = nrec - 1;
+    const double t_now_i = times[idx];
+    const double t_old_i = idx == 0 ? times[0] : times[idx - 1];
+    const double dstep = t_now_i - t_old_i;
+    const double x = (t - t_old_i) / dstep;
+    const unsigned long long n = p.n;
+    const double* rec = p.dense_state + (traj * p.dense_cap + idx) * n * (QO + 1);
+    double* out = p.out + pair * n;
+    for (unsigned i = threadIdx.x; i < p.n; i += blockDim.x) {
+        double qv[QO];
+#pragma unroll
+        for (int k = 0; k < QO; k++) qv[k] = rec[n * (1 + k) + i];
+        double y;
+        if constexpr (!Tab::IS_DOP) {
+            double cp = x;
+            double acc = qv[0] * cp;
+#pragma unroll
+            for (int pw = 1; pw < QO; pw++) { cp *= x; acc += qv[pw] * cp; }
+            acc *= dstep;
+            y = rec[i] + acc;
+        } else {
+            double acc = qv[0];
+            acc *= x;
+            acc += qv[1]; acc *= (1.0 - x);
+            acc += qv[2]; acc *= x;
+            acc += qv[3]; acc *= (1.0 - x);
+            acc += qv[4]; acc *= x;
+            acc += qv[5]; acc *= (1.0 - x);
+            acc += qv[6]; acc *= x;
+            y = rec[i] + acc;
+        }
+        out[i] = y;
+    }
+}
+
+template <int METHOD>
+__global__ void cta_dense_eval_kernel(const __grid_constant__ CtaDenseEvalParams p)
+{
+    cta_dense_eval_body<METHOD>(p);
 }
 
 }  // namespace CYRK_FP_NS

@@ -31,9 +31,34 @@ struct CtaParams {
     double*   t_rows;            // [n_traj][row_cap]
     double*   y_rows;            // [n_traj][row_cap][n]
     unsigned  row_cap;
+    // ---- dense store (register-resident kernel only): interpolant k covers (dense_t[k-1], dense_t[k]]; one record is
+    //      [y_old[n] | Q_0[n] | ... | Q_{QO-1}[n]] (coefficient-major, so every store and load is coalesced)
+    int       dense_output;
+    double*   dense_t;           // [n_traj][dense_cap]
+    double*   dense_state;       // [n_traj][dense_cap][n * (Q_ORDER + 1)]
+    unsigned* dense_count;       // [n_traj]
+    unsigned  dense_cap;
     double*   scratch;           // [gridDim.x][n_vec_global + 1][n_pad]: spilled vectors + the problem's aux table
     unsigned  n_smem_vec;        // how many of the working vectors live in shared memory
     unsigned long long* queue;
+};
+
+// Post-hoc dense evaluation of a CTA-path solution (CySolverResult::call_vectorize, cysolution.cpp:511-616): one CTA per
+// (trajectory, query time), threads stride over the components.
+struct CtaDenseEvalParams {
+    unsigned long long n_traj;
+    unsigned n;
+    const double* t_query;       // [n_query] shared
+    unsigned      n_query;
+    const double* t_span;
+    unsigned      t_span_stride;
+    const int*      status;
+    const double*   dense_t;
+    const double*   dense_state;
+    const unsigned* dense_count;
+    unsigned        dense_cap;
+    double*       out;           // [n_traj][n_query][n]
+    int*          code;          // [n_traj]  first non-zero CySolverResult::call status, else 0
 };
 
 // ---- register-resident kernel (cta2_core.cuh): compile-time placement of the stage derivatives K_0..K_{nkd-1}

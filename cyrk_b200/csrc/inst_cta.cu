@@ -77,6 +77,17 @@ cudaError_t CYRK_CAT2(cta2_launch_, CYRK_FP_NS)(int rhs_id, int method, int C, c
     return cudaErrorInvalidValue;
 }
 
+cudaError_t CYRK_CAT2(cta_dense_eval_, CYRK_FP_NS)(int method, const CtaDenseEvalParams& p, int grid, int block, cudaStream_t s)
+{
+    switch (method) {
+    case METHOD_RK23: CYRK_FP_NS::cta_dense_eval_kernel<METHOD_RK23><<<grid, block, 0, s>>>(p); break;
+    case METHOD_RK45: CYRK_FP_NS::cta_dense_eval_kernel<METHOD_RK45><<<grid, block, 0, s>>>(p); break;
+    case METHOD_DOP853: CYRK_FP_NS::cta_dense_eval_kernel<METHOD_DOP853><<<grid, block, 0, s>>>(p); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 #if !CYRK_FP_STRICT
 int cta_num_vectors(int method)
 {

@@ -71,9 +71,9 @@ def test_largey_simple_and_unsupported_features():
     # dy_0 = sin(2 pi t / 10), the rest is constant: y_0(10) = 100 + (10/2pi)(1 - cos(2 pi)) = 100
     assert np.allclose(r.y_last[:, 0], 100.0, atol=5e-3) and np.all(r.y_last[:, 1:] == 100.0)
     with pytest.raises(c.CyrkB200Error):
-        c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, args=[-0.5, float(n)], dense_output=True)
-    with pytest.raises(c.CyrkB200Error):
         c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, args=[-0.5, float(n)], events=[c.Event("y0")])
+    with pytest.raises(c.CyrkB200Error):        # stored dense output needs the register-resident kernel (n_y <= 4096)
+        c.cysolve_ivp_batch("largey", (0.0, 10.0), 100.0 * np.ones((2, 5000)), args=[-0.5, 5000.0], dense_output=True)
 
 
 @pytest.mark.parametrize("n", [700, 1500, 3000, 5000])
@@ -147,4 +147,36 @@ def test_cta_results_are_bitwise_reproducible():
             ref = cur
         else:
             assert all(np.array_equal(a, b) for a, b in zip(ref, cur))
+        r.close()
+
+
+@pytest.mark.parametrize("method", ["RK23", "RK45", "DOP853"])
+@pytest.mark.parametrize("n", [130, 1500])
+def test_cta_dense_output_matches_oracle(oracle, method, n):
+    """dense_output=True on the CTA path: sol(t) from the stored interpolants vs the oracle's CySolverResult::call, forward
+    and backward, with and without t_eval; nfev includes DOP853's three extra evaluations per interpolant."""
+    rng = np.random.default_rng(31)
+    B = 3
+    y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (B, n)))
+    args = [-0.5, float(n)]
+    for span, t_eval in (((0.0, 6.0), None), ((6.0, 0.0), None), ((0.0, 6.0), np.linspace(0.0, 6.0, 5))):
+        tq = np.array([0.0, 0.37, 2.5, 5.99, 6.0])
+        r = c.cysolve_ivp_batch("largey", span, y0, method=method, args=args, rtol=1e-6, atol=1e-8, dense_output=True,
+                                t_eval=t_eval, expected_size=4)          # tiny capacity: exercises the exact-capacity re-run
+        out, codes = r.call(tq)
+        assert (codes == 0).all() and out.shape == (B, tq.size, n)
+        for i in (0, B - 1):
+            ref = oracle.solve("largey", span, y0[i], method, 1e-6, 1e-8, args=args, dense_output=True, t_eval=t_eval, call_t=tq)
+            v = r[i]
+            assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken)
+            assert int(r.nfev[i]) == ref.nfev
+            got = out[i].T                                           # (n, len(tq)) like sol(t)
+            # (backward runs: the reference's lookup lands on the degenerate interpolant #0 at t = t_start -> NaN; kept)
+            nan = np.isnan(ref.dense)
+            assert np.array_equal(np.isnan(got), nan)
+            assert np.all(np.abs(got - ref.dense)[~nan] <= _tol(ref.dense, 1e-6, 1e-8)[~nan]), (method, n, span)
+            assert np.allclose(v(tq), got, equal_nan=True)
+        # outside the span -> ARGUMENT_ERROR (-21... the reference's code), per trajectory
+        _, bad = r.call(np.array([7.0]))
+        assert (bad != 0).all()
         r.close()
