@@ -88,6 +88,8 @@ static int g_opt_prep = -1;           // -1 = automatic (n_traj >= 2 Mi), 1 = al
 static int g_opt_block = 0;            // threads per CTA of the thread-per-trajectory kernels; 0 = pick by occupancy (128 or 96)
 static int g_opt_cta_smem_vecs = -1;  // CTA path: working vectors kept in shared memory (-1 = as many as fit)
 static int g_opt_cta_block = 0;       // CTA path: threads per CTA (0 = by n_y)
+static int g_opt_pipe_taper = 1;       // pipelined host-I/O path: short first / last chunks
+static int g_opt_pipe_chunk = 1 << 20; // pipelined host-I/O path: trajectories per chunk (at most 32 chunks)
 static int g_opt_cta_kernel = 0;      // CTA path: 0 = register-resident kernel where it applies, 1 = always the shared-memory/slab kernel
 static int g_opt_root_batch = 12;     // measured: 8..16 is the flat optimum on the C3 workload (profiles/r01_notes.md)
 static int g_opt_ctas_per_sm = 0;
@@ -343,8 +345,21 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
 {
     const size_t B = a.n_traj, NY = pe->ny, NDY = pe->ny + pe->nextra;
     const size_t args_stride = (size_t)pe->nargs_dbl * sizeof(double);
-    size_t chunk = std::max<size_t>(size_t(1) << 20, (B + 15) / 16);
-    const size_t nchunk = (B + chunk - 1) / chunk;
+    // Chunk schedule: full chunks in the middle, a short one in front (the first copy-in is not overlapped with any
+    // compute) and two short ones at the end (the last copy-out is not overlapped either).
+    const size_t chunk = std::max<size_t>((size_t)g_opt_pipe_chunk, (B + 31) / 32);
+    std::vector<std::pair<size_t, size_t>> sched;          // (offset, count)
+    {
+        size_t off = 0;
+        auto push = [&](size_t n) { n = std::min(n, B - off); if (n) { sched.emplace_back(off, n); off += n; } };
+        const bool taper = g_opt_pipe_taper && B >= 4 * chunk;
+        const size_t tail = taper ? chunk / 2 + chunk / 4 : 0;
+        if (taper) push(chunk / 4);
+        while (B - off > tail + chunk / 2) push(chunk);
+        push(B - off - std::min(tail, B - off));
+        if (taper) { push(chunk / 2); push(chunk / 4); }
+    }
+    const size_t nchunk = sched.size();
     if (h->events(4 * nchunk)) return -1;
     if (h->d_y0.ensure(B * NY * 8) || h->d_queue.ensure(8 * nchunk)) return -1;
     if (use_prep && h->d_prep.ensure(B * (NDY + 2) * 8)) return -1;
@@ -384,7 +399,7 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
     h->tspan_stride = p.t_span_stride; h->args_stride = p.args_stride;
 
     for (size_t c = 0; c < nchunk; c++) {
-        const size_t off = c * chunk, n = std::min(chunk, B - off);
+        const size_t off = sched[c].first, n = sched[c].second;
         cudaEvent_t e_in = h->ev_pool[4 * c], e_k0 = h->ev_pool[4 * c + 1], e_k1 = h->ev_pool[4 * c + 2];
         cudaStream_t sc = (c & 1) ? h->s_comp2 : h->stream;
         // ---- copy in
@@ -1329,6 +1344,8 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
     if (!strcmp(name, "cta_kernel")) { g_opt_cta_kernel = value; return 0; }
+    if (!strcmp(name, "pipe_taper")) { g_opt_pipe_taper = value; return 0; }
+    if (!strcmp(name, "pipe_chunk")) { if (value < 1024) { set_error("pipe_chunk must be >= 1024"); return -1; } g_opt_pipe_chunk = value; return 0; }
     set_error("unknown option '%s'", name);
     return -1;
 }
