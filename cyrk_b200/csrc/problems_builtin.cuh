@@ -56,7 +56,16 @@ __device__ __forceinline__ double builtin_event(int id, double t, const double* 
     }
 }
 
+// Problems may append NDERIVED doubles to their per-trajectory argument registers: derive(a) runs once when a
+// trajectory is loaded and fills a[NARGS_DBL ..] from a[0 .. NARGS_DBL) -- coefficients the reference recomputes in
+// every right-hand-side call (two FP64 divisions per call for the pendulum: ~70 instructions per RK23 attempt).  The
+// operations are the reference's, only hoisted, so the strict build stays bit-identical.
 #define CYRK_PROBLEM_COMMON(ny, nx, nargs)                                                        \
+    CYRK_PROBLEM_HEAD(ny, nx, nargs)                                                              \
+    static constexpr int NDERIVED = 0;                                                            \
+    __device__ __forceinline__ static void derive(double*) {}
+
+#define CYRK_PROBLEM_HEAD(ny, nx, nargs)                                                          \
     static constexpr int NY = ny;                                                                 \
     static constexpr int NEXTRA = nx;                                                             \
     static constexpr int NARGS_DBL = nargs;                                                       \
@@ -153,13 +162,18 @@ struct ProbLotkaVolterra {      // cysolver_test.pyx:104-118, Performance/lotkav
 struct ProbPendulum {           // cysolver_test.pyx:122-141, Performance/pendulum.py:8-25
     // args (l, m, g) plus two spare doubles so the per-trajectory stop-time events
     // (EV_T_MINUS_ARG4 / EV_ABS_Y0_MINUS_ARG4) can be used with the undamped pendulum too.
-    CYRK_PROBLEM_COMMON(2, 0, 5)
+    CYRK_PROBLEM_HEAD(2, 0, 5)
+    static constexpr int NDERIVED = 2;
+    __device__ __forceinline__ static void derive(double* a)
+    {
+        const double l = a[0], m = a[1], g = a[2];
+        a[5] = (-3. * g / (2. * l));
+        a[6] = (3. / (m * (l * l)));
+    }
     __device__ __forceinline__ static void rhs(double* dy, double t, const double* y, const char* args)
     {
         const double* p = reinterpret_cast<const double*>(args);
-        const double l = p[0], m = p[1], g = p[2];
-        const double coeff_1 = (-3. * g / (2. * l));
-        const double coeff_2 = (3. / (m * (l * l)));
+        const double coeff_1 = p[5], coeff_2 = p[6];
         const double y0 = y[0], y1 = y[1];
         const double torque = 0.1 * CYRK_FP_NS::psin(t);
         dy[0] = y1;
@@ -209,13 +223,19 @@ struct ProbPendulumPreEval {    // cysolver_test.pyx:182-222: the pre-eval hook 
 };
 
 struct ProbPendulumDrag {       // Documentation/Advanced_CySolver.md:127-152; args (l, m, g, c, stop)
-    CYRK_PROBLEM_COMMON(2, 1, 5)
+    CYRK_PROBLEM_HEAD(2, 1, 5)
+    static constexpr int NDERIVED = 2;
+    __device__ __forceinline__ static void derive(double* a)
+    {
+        const double l = a[0], m = a[1], g = a[2];
+        a[5] = (-3. * g / (2. * l));
+        a[6] = (3. / (m * (l * l)));
+    }
     __device__ __forceinline__ static void rhs(double* dy, double t, const double* y, const char* args)
     {
         const double* p = reinterpret_cast<const double*>(args);
-        const double l = p[0], m = p[1], g = p[2], c = p[3];
-        const double coeff_1 = (-3. * g / (2. * l));
-        const double coeff_2 = (3. / (m * (l * l)));
+        const double c = p[3];
+        const double coeff_1 = p[5], coeff_2 = p[6];
         const double y0 = y[0], y1 = y[1];
         const double torque = 0.1 * CYRK_FP_NS::psin(t);
         dy[0] = y1;
