@@ -208,7 +208,11 @@ double   cyrk_b200_get_total_ms(void* h);       /* CUDA-event time H2D -> kernel
 unsigned cyrk_b200_get_launch_count(void* h);   /* kernels launched by the last call                        */
 size_t   cyrk_b200_get_h2d_bytes(void* h);
 size_t   cyrk_b200_get_d2h_bytes(void* h);
-/* Tuning knobs: "refill_min" (1..32), "block" (threads per CTA), "ctas_per_sm" (0 = occupancy API). */
+/* Tuning knobs (process-wide): "refill_min" (1..32), "block" (threads per CTA of the thread-per-trajectory kernels,
+ * 0 = by occupancy), "ctas_per_sm" (0 = occupancy API), "prep" (start-up kernel: -1 auto / 0 / 1), "root_batch" (1..32),
+ * "cta_kernel" (0 = register-resident CTA kernel where it applies, 1 = shared-memory/slab kernel), "cta_block",
+ * "cta_smem_vecs" (slab kernel only), "pipe_chunk" (trajectories per chunk of the pipelined host-I/O path),
+ * "pipe_taper" (short first/last chunks, 0/1). */
 int      cyrk_b200_set_option(const char* name, int value);
 /* FP64 FMA throughput probe (dependent-free DFMA streams on every SM): returns TFLOP/s. */
 double   cyrk_b200_measure_fp64_tflops(int device);
