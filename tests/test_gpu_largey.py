@@ -180,3 +180,31 @@ def test_cta_dense_output_matches_oracle(oracle, method, n):
         _, bad = r.call(np.array([7.0]))
         assert (bad != 0).all()
         r.close()
+
+
+def test_cta_failure_statuses_match_oracle(oracle):
+    """Failure paths of the CTA kernels end with the reference's status codes (and never hang): max_num_steps (-52),
+    a NaN initial state (step size collapses: -54), a bad first_step (-80, clean instead of the reference's crash)."""
+    rng = np.random.default_rng(41)
+    n = 700
+    y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (3, n)))
+    args = [-0.5, float(n)]
+    for kernel in (0, 1):
+        c.lib().cyrk_b200_set_option(b"cta_kernel", kernel)
+        try:
+            # user cap on the number of steps
+            r = c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method="RK45", args=args, rtol=1e-6, atol=1e-8, max_num_steps=5)
+            ref = oracle.solve("largey", (0.0, 10.0), y0[0], "RK45", 1e-6, 1e-8, args=args, max_num_steps=5)
+            assert ref.status == -52 and (r.status == ref.status).all() and (r.steps_taken == ref.steps_taken).all()
+            # NaN in the initial state of ONE trajectory: that one fails, its neighbours are untouched
+            bad = y0.copy(); bad[1, 17] = np.nan
+            r = c.cysolve_ivp_batch("largey", (0.0, 10.0), bad, method="RK45", args=args, rtol=1e-6, atol=1e-8)
+            ref = oracle.solve("largey", (0.0, 10.0), bad[1], "RK45", 1e-6, 1e-8, args=args)
+            good = oracle.solve("largey", (0.0, 10.0), bad[0], "RK45", 1e-6, 1e-8, args=args)
+            assert r.status[1] == ref.status and ref.status < 0
+            assert r.status[0] == 1 and r.status[2] == 1 and r.steps_taken[0] == good.steps_taken
+            # first_step larger than half the span
+            r = c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method="RK45", args=args, rtol=1e-6, atol=1e-8, first_step=6.0)
+            assert (r.status == -80).all() and (r.steps_taken == 0).all()
+        finally:
+            c.lib().cyrk_b200_set_option(b"cta_kernel", 0)
