@@ -723,13 +723,12 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     const bool device_io = (a.flags & CYRK_FLAG_DEVICE_IO) != 0;
     const bool want_rows = a.store_mode == CYRK_STORE_ROWS;
     if (a.num_extra != 0) { set_error("the CTA-per-trajectory path does not capture extra outputs yet"); return -1; }
-    if (a.n_events != 0) { set_error("the CTA-per-trajectory path does not support events yet"); return -1; }
     const bool dense = a.dense_output != 0;
     const bool user_rhs = a.rhs_id >= CYRK_RHS_USER_BASE;
     if (!user_rhs && (a.n_args == 0 || a.args_len < 8)) { set_error("largey problems need args = (decay_rate, ...)"); return -1; }
     if (N > 0x7fffffffu) { set_error("n_y too large"); return -1; }
     h->ny = N; h->nx = 0; h->ndy = N; h->q_order = 0;
-    h->n_traj = B; h->n_events = 0; h->n_t_eval = a.n_t_eval;
+    h->n_traj = B; h->n_events = a.n_events; h->n_t_eval = a.n_t_eval;
     h->dense_output = dense; h->device_io = device_io; h->cta_path = true;
     h->q_order = a.method == CYRK_METHOD_RK23 ? 3 : a.method == CYRK_METHOD_RK45 ? 4 : 7;
     h->h2d_bytes = h->d2h_bytes = 0; h->launches = 0; h->kernel_ms = 0.f;
@@ -810,6 +809,16 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         p.rtol0 = rt[0];
         p.atol0 = at[0];
     }
+    if (a.n_events && !use_cta2) {
+        set_error("events on the CTA-per-trajectory path need the register-resident kernel (n_y <= %d)", 8 * cta2_max_block);
+        return -1;
+    }
+    p.n_events = (int)a.n_events;
+    for (size_t e = 0; e < a.n_events; e++) {
+        p.ev_id[e] = a.event_ids[e];
+        p.ev_dir[e] = a.event_dirs ? a.event_dirs[e] : 0;
+        p.ev_max[e] = a.event_max ? (unsigned long long)a.event_max[e] : ~0ull;
+    }
     if (dense && !use_cta2) {
         set_error("stored dense output on the CTA-per-trajectory path needs the register-resident kernel (n_y <= %d); use t_eval", 8 * cta2_max_block);
         return -1;
@@ -826,7 +835,7 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         const size_t by_smem = std::max<size_t>(1, (size_t)smem_per_sm / (smem + 2048));
         const int per_sm = (int)std::min<size_t>({(size_t)8, by_regs, by_smem});
         grid = (int)std::min<unsigned long long>((unsigned long long)device_sm_count(h->device) * per_sm, B);
-        const size_t ngl = (size_t)std::max(1, cta2_ngl(nkd, cta2_C));
+        const size_t ngl = (size_t)std::max(1, cta2_ngl(nkd, cta2_C)) + 1;      // + one vector for event root searches
         if (h->d_scratch.ensure((size_t)grid * ngl * V * 8)) return -1;
         p.scratch = h->d_scratch.as<double>();
     } else {
@@ -851,9 +860,10 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         p.scratch = h->d_scratch.as<double>();
     }
 
-    size_t row_cap = 0, dense_cap = 0;
+    size_t row_cap = 0, dense_cap = 0, ev_cap = 0;
     if (want_rows) row_cap = a.n_t_eval ? a.n_t_eval : (a.expected_size ? a.expected_size : 64);
     if (dense) dense_cap = a.expected_size ? a.expected_size : 64;
+    if (a.n_events) ev_cap = a.expected_size ? a.expected_size : 8;      // one hit record is n_y + 1 doubles: start small
     for (int pass = 0; pass < 2; pass++) {
         if (want_rows) {
             if (h->d_trows.ensure(B * row_cap * 8) || h->d_yrows.ensure(B * row_cap * N * 8)) return -1;
@@ -867,6 +877,14 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
             p.dense_output = 1;
             p.dense_t = h->d_dense_t.as<double>(); p.dense_state = h->d_dense_state.as<double>();
             p.dense_count = h->d_dense_count.as<unsigned>(); p.dense_cap = (unsigned)dense_cap;
+        }
+        if (a.n_events) {
+            if (h->d_ev_t.ensure(B * a.n_events * ev_cap * 8) || h->d_ev_y.ensure(B * a.n_events * ev_cap * N * 8) ||
+                h->d_ev_count.ensure(B * a.n_events * 4) || h->d_ev_term.ensure(B * 4) || h->h_ev_count.ensure(B * a.n_events * 4))
+                return -1;
+            p.ev_t = h->d_ev_t.as<double>(); p.ev_y = h->d_ev_y.as<double>();
+            p.ev_count = h->d_ev_count.as<unsigned>(); p.ev_term_index = h->d_ev_term.as<int>();
+            p.ev_cap = (unsigned)ev_cap;
         }
         CU_TRY(cudaMemsetAsync(h->d_queue.p, 0, 8, h->stream));
         CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
@@ -887,24 +905,31 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
         if ((want_rows || !device_io) && download(h, h->h_size, h->d_size, B * 4)) return -1;
         if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
+        if (a.n_events && download(h, h->h_ev_count, h->d_ev_count, B * a.n_events * 4)) return -1;
         CU_TRY(cudaStreamSynchronize(h->stream));
         { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; }
-        if (!want_rows && !dense) break;
-        size_t mx = 0, mxd = 0;
+        if (!want_rows && !dense && !a.n_events) break;
+        size_t mx = 0, mxd = 0, mxe = 0;
+        if (a.n_events) { const unsigned* ec = h->h_ev_count.as<unsigned>(); for (size_t i = 0; i < B * a.n_events; i++) mxe = std::max<size_t>(mxe, ec[i]); }
         if (want_rows) { const unsigned* sz = h->h_size.as<unsigned>(); for (size_t i = 0; i < B; i++) mx = std::max<size_t>(mx, sz[i]); }
         if (dense) { const unsigned* dc = h->h_dense_count.as<unsigned>(); for (size_t i = 0; i < B; i++) mxd = std::max<size_t>(mxd, dc[i]); }
-        if (mx <= row_cap && mxd <= dense_cap) break;
+        if (mx <= row_cap && mxd <= dense_cap && mxe <= ev_cap) break;
         if (pass == 1) { set_error("internal: arena overflow after the exact-capacity re-run"); return -1; }
         row_cap = std::max(row_cap, mx);
         dense_cap = std::max(dense_cap, mxd);
+        ev_cap = std::max(ev_cap, mxe);
     }
-    h->row_cap = row_cap; h->dense_cap = dense_cap; h->ev_cap = 0;
+    h->row_cap = row_cap; h->dense_cap = dense_cap; h->ev_cap = ev_cap;
     if (!device_io) {
         if (download(h, h->h_status, h->d_status, B * 4) || download(h, h->h_steps, h->d_steps, B * 4) ||
             download(h, h->h_nrej, h->d_nrej, B * 4) || download(h, h->h_nfev, h->d_nfev, B * 4) ||
             download(h, h->h_tlast, h->d_tlast, B * 8) || download(h, h->h_ylast, h->d_ylast, B * N * 8))
             return -1;
         if (want_rows && (download(h, h->h_trows, h->d_trows, B * row_cap * 8) || download(h, h->h_yrows, h->d_yrows, B * row_cap * N * 8)))
+            return -1;
+        if (a.n_events && (download(h, h->h_ev_t, h->d_ev_t, B * a.n_events * ev_cap * 8) ||
+                           download(h, h->h_ev_y, h->d_ev_y, B * a.n_events * ev_cap * N * 8) ||
+                           download(h, h->h_ev_term, h->d_ev_term, B * 4)))
             return -1;
     }
     CU_TRY(cudaEventRecord(h->ev_end, h->stream));

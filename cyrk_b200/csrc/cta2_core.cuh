@@ -21,7 +21,10 @@
 // rk.cpp:1047-1072): an O(eps*sqrt(n_y)) difference, documented in DESIGN.md.
 //
 // Stored dense output: one coalesced record [y_old | Q_0 | .. | Q_{QO-1}] per accepted step, evaluated afterwards by
-// cta_dense_eval_kernel.  Not available on this path (the host shim rejects them): extra outputs, events.
+// cta_dense_eval_kernel.  Events: the values g_e(t, y) are evaluated by thread 0 on the complete vector and published
+// through shared memory; every thread then runs the reference's trigger logic and Brent iteration redundantly (identical
+// inputs -> identical branches), interpolating its own components of the state for each evaluation.  Not available on
+// this path (the host shim rejects it): extra outputs.
 #pragma once
 #include "rk_core.cuh"
 #include "cta_core_params.h"
@@ -29,7 +32,9 @@
 namespace cyrk {
 namespace CYRK_FP_NS {
 
-template <class Prob, int METHOD, int C>
+// EVENTS: compiled with the event machinery (a separate instantiation: its per-event state and extra pointers would
+// otherwise push the event-free kernel over its 128-register budget).
+template <class Prob, int METHOD, int C, bool EVENTS>
 struct Cta2Solver {
     using Tab = typename TabFor<METHOD>::type;
     using Ld = TabLd<Tab>;
@@ -50,7 +55,10 @@ struct Cta2Solver {
     double kr[NREG > 0 ? NREG : 1][C];
     double* buf0; double* buf1;  // stage-input buffers (shared memory), V doubles each (no run-time indexed member arrays:
                                  // they would drag the whole solver state into local memory)
-    double* ybuf;                // the buffer that holds y_now (last y_new computed, or y0)
+    double* ybuf;                // the buffer that holds y_now (last y_new computed, or y0; the terminal state after an event)
+    const double* ystep;         // y_new of the step just taken (the interpolant's end point; == ybuf except after termination)
+    double* gsh;                 // shared memory [1 + CYRK_MAX_EVENTS]: event values published by thread 0
+    double* xbuf;                // global scratch vector [V]: the interpolated state at xb during a root search
     double* aux;                 // [V] shared memory
     double* ksm;                 // [NSM][V] shared memory
     double* kgl;                 // [NGL][V] global slab
@@ -180,6 +188,7 @@ struct Cta2Solver {
         __syncthreads();
         eval_rhs<NS>(t_now, in);
         ybuf = in;
+        ystep = in;
     }
 
     // rk.cpp:778-823, 1027-1075, 1414-1489.  Strict build: returns err (reference formulas).  Production build:
@@ -302,7 +311,7 @@ struct Cta2Solver {
             const double q1 = h * dot_k<DRow<2>, 16>(c, DRow<2>{});
             const double q2 = h * dot_k<DRow<1>, 16>(c, DRow<1>{});
             const double q3 = h * dot_k<DRow<0>, 16>(c, DRow<0>{});
-            const double delta_y = ybuf[comp(c)] - yo[c];
+            const double delta_y = (EVENTS ? ystep : ybuf)[comp(c)] - yo[c];
             const double sum_dy = kget<NS>(c) + kget<0>(c);
             const double q4 = 2.0 * delta_y - h * sum_dy;
             const double q5 = h * kget<0>(c) - delta_y;
@@ -385,7 +394,7 @@ struct Cta2Solver {
                         q[1] = step * dot_k<DRow<2>, 16>(c, DRow<2>{});
                         q[2] = step * dot_k<DRow<1>, 16>(c, DRow<1>{});
                         q[3] = step * dot_k<DRow<0>, 16>(c, DRow<0>{});
-                        const double delta_y = ybuf[i] - yo[c];
+                        const double delta_y = (EVENTS ? ystep : ybuf)[i] - yo[c];
                         const double sum_dy = kget<NS>(c) + kget<0>(c);
                         q[4] = 2.0 * delta_y - step * sum_dy;
                         q[5] = step * kget<0>(c) - delta_y;
@@ -397,6 +406,79 @@ struct Cta2Solver {
             }
         }
         n_dense++;
+    }
+
+    // ---------------------------------------------------------------- events
+    // g_e(t, y) for a state `y` that every thread has finished writing its components of; all threads get the value.
+    CYRK_DI double event_value(const CtaParams& p, int e, double t, const double* y)
+    {
+        __syncthreads();                     // y is complete; everybody has read the previous gsh[0]
+        if (tid == 0) gsh[0] = Prob::event(p.ev_id[e], t, y, n, args);
+        __syncthreads();
+        return gsh[0];
+    }
+    // own components of the step's interpolant at time t (dense.cpp:71-170) into dst
+    CYRK_DI void interp_into(double* dst, double t, double told, double h) const
+    {
+        const double x = (t - told) / h;
+#pragma unroll
+        for (int c = 0; c < C; c++) dst[comp(c)] = interp_component(c, x, h);
+    }
+
+    // c_brentq.cpp:41-204 over [xa, xb] for event e, restated like TrajSolver::root_step / brent_advance (rk_core.cuh).
+    // `scr` ends up holding the state of the LAST evaluation that went through it (the reference reports that buffer,
+    // SURVEY 8a quirk 5).  Returns the error code (ST_CONVERGED = found) and the root.
+    CYRK_DI int brentq(const CtaParams& p, int e, double xa, double xb, double told, double h, double* scr, double& root)
+    {
+        const double xtol = 4.0 * CYRK_EPS, rtol = 4.0 * CYRK_EPS;
+        double xpre = xa, xcur = xb, xblk = 0., fblk = 0., spre = 0., scur = 0.;
+        interp_into(scr, xpre, told, h);
+        double fpre = event_value(p, e, xpre, scr);
+        if (fpre == 0) { root = xpre; return ST_CONVERGED; }
+        interp_into(xbuf, xcur, told, h);
+        double fcur = event_value(p, e, xcur, xbuf);
+        if (fcur == 0) {
+#pragma unroll
+            for (int c = 0; c < C; c++) scr[comp(c)] = xbuf[comp(c)];
+            root = xcur;
+            return ST_CONVERGED;
+        }
+        if (sign_bit(fpre) == sign_bit(fcur)) { root = 0.0; return ST_OPTIMIZE_SIGN_ERROR; }
+        for (int iter = 0; iter < 100; iter++) {
+            if ((fpre != 0) && (fcur != 0) && (sign_bit(fpre) != sign_bit(fcur))) {
+                xblk = xpre; fblk = fpre;
+                spre = scur = xcur - xpre;
+            }
+            if (fabs(fblk) < fabs(fcur)) {
+                xpre = xcur; xcur = xblk; xblk = xpre;
+                fpre = fcur; fcur = fblk; fblk = fpre;
+            }
+            const double delta = (xtol + rtol * fabs(xcur)) / 2.0;
+            const double sbis = (xblk - xcur) / 2.0;
+            if ((fcur == 0) || (fabs(sbis) < delta)) { root = xcur; return ST_CONVERGED; }
+            if ((fabs(spre) > delta) && (fabs(fcur) < fabs(fpre))) {
+                double stry;
+                if (xpre == xblk) {
+                    stry = -fcur * (xcur - xpre) / (fcur - fpre);
+                } else {
+                    const double dpre = (fpre - fcur) / (xpre - xcur);
+                    const double dblk = (fblk - fcur) / (xblk - xcur);
+                    stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+                }
+                const double m_a = fabs(spre), m_b = 3.0 * fabs(sbis) - delta;
+                if (2.0 * fabs(stry) < (m_a < m_b ? m_a : m_b)) { spre = scur; scur = stry; }
+                else { spre = sbis; scur = sbis; }
+            } else {
+                spre = sbis; scur = sbis;
+            }
+            xpre = xcur; fpre = fcur;
+            if (fabs(scur) > delta) xcur += scur;
+            else xcur += (sbis > 0 ? delta : -delta);
+            interp_into(scr, xcur, told, h);
+            fcur = event_value(p, e, xcur, scr);
+        }
+        root = xcur;
+        return ST_OPTIMIZE_CONVERGENCE_ERROR;
     }
 
     // whole trajectory (cysolver.cpp:303-543 setup, 752-1000 loop)
@@ -413,6 +495,7 @@ struct Cta2Solver {
         inv_n = 1.0 / (double)n;
         const double* y0 = p.y0 + traj * n;
         ybuf = buf0;
+        ystep = buf0;
         __syncthreads();                                   // the previous trajectory's readers are done with the buffers
 #pragma unroll
         for (int c = 0; c < C; c++) {
@@ -427,6 +510,19 @@ struct Cta2Solver {
         eval_rhs<0>(t_now, ybuf);                          // RHS evaluation #1
         if (p.n_t_eval == 0) save_row_from_ybuf(p, traj, t_now);
         te_old = fwd ? 0u : p.n_t_eval;
+        // per-event state, replicated in every thread (all copies evolve identically)
+        constexpr int NEV = EVENTS ? CYRK_MAX_EVENTS : 1;
+        double g_old[NEV], ev_root[NEV];
+        unsigned long long ev_seen[NEV];
+        unsigned ev_hits[NEV];
+        bool event_terminated = false;
+        int term_index = -1;
+        if constexpr (EVENTS) {
+            if (tid == 0)
+                for (int e = 0; e < p.n_events; e++) gsh[1 + e] = Prob::event(p.ev_id[e], t_now, ybuf, n, args);
+            __syncthreads();
+            for (int e = 0; e < p.n_events; e++) { g_old[e] = gsh[1 + e]; ev_seen[e] = 0; ev_hits[e] = 0; ev_root[e] = 0.0; }
+        }
         if (p.dense_output) {
             // interpolant #0 at t0: Q == 0 (quirk 9); DOP853 spends its three extra evaluations on it in the reference
             store_dense(p, traj, true);
@@ -495,9 +591,83 @@ struct Cta2Solver {
                 extra_done = true;
                 store_dense(p, traj, false);
             }
+            const double h_step = t_now - t_old;          // the interpolant's (t_old, step): t_now may move to an event root
+            const double t_step_old = t_old;
+            bool extra_counted = false;
+            if constexpr (EVENTS) {                        // p_check_events, cysolver.cpp:563-750
+                if (tid == 0)
+                    for (int e = 0; e < p.n_events; e++) gsh[1 + e] = Prob::event(p.ev_id[e], t_now, ybuf, n, args);
+                __syncthreads();
+                unsigned mask = 0;
+                for (int e = 0; e < p.n_events; e++) {
+                    const double g_now = gsh[1 + e];
+                    const double go = g_old[e];
+                    const bool up = (go <= 0.0) && (g_now >= 0.0);
+                    const bool down = (go >= 0.0) && (g_now <= 0.0);         // 0 -> 0 triggers (quirk 4)
+                    const int dir = p.ev_dir[e];
+                    const bool trig = (dir == 0 && (up || down)) || (dir > 0 && up) || (dir < 0 && down);
+                    g_old[e] = g_now;
+                    if (trig) { ev_seen[e]++; mask |= (1u << e); }
+                }
+                if constexpr (Tab::IS_DOP) {
+                    // the reference builds the interpolant on every step with events: three more evaluations
+                    if (!extra_done) {
+                        if (mask != 0u) { dense_extra_stages(); extra_done = true; }
+                        else { nfev += 3; extra_counted = true; }
+                    }
+                }
+                if (mask != 0u) {
+                    double* scr = (ybuf == buf0) ? buf1 : buf0;
+                    double term_root = fwd ? d_inf() : -d_inf();
+                    for (int e = 0; e < p.n_events && !error_flag; e++) {
+                        if (!(mask & (1u << e))) continue;
+                        double root = 0.0;
+                        const int err = brentq(p, e, t_old, t_now, t_step_old, h_step, scr, root);
+                        if (err != ST_CONVERGED) { error_flag = true; status = err; break; }
+                        ev_root[e] = root;
+                        if (p.ev_t != nullptr && ev_hits[e] < p.ev_cap) {      // slot ev_hits[e]; committed below
+                            const unsigned long long r = (traj * p.n_events + e) * (unsigned long long)p.ev_cap + ev_hits[e];
+                            if (tid == 0) p.ev_t[r] = root;
+                            double* dst = p.ev_y + r * n;
+#pragma unroll
+                            for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) dst[i] = scr[i]; }
+                        }
+                        if (ev_seen[e] >= p.ev_max[e]) {
+                            event_terminated = true;
+                            if (fwd) { if (root < term_root) term_root = root; }
+                            else     { if (root > term_root) term_root = root; }
+                        }
+                    }
+                    if (!error_flag) {
+                        // keep the hits that are not beyond the termination root (cysolver.cpp:706-748)
+                        for (int e = 0; e < p.n_events; e++) {
+                            if (!(mask & (1u << e))) continue;
+                            if (event_terminated) {
+                                if (ev_root[e] == term_root) term_index = e;
+                                const bool beyond = fwd ? (ev_root[e] > term_root) : (ev_root[e] < term_root);
+                                if (beyond) continue;
+                            }
+                            ev_hits[e]++;
+                        }
+                        status = ST_NO_ERROR;
+                        if (event_terminated) {
+                            status = ST_EVENT_TERMINATED;
+                            if (t_now != term_root) {
+                                // the trajectory ends at the root: its state is the interpolant there (cysolver.cpp:812-836)
+                                __syncthreads();               // thread 0 may still be reading scr
+                                t_now = term_root;
+                                interp_into(scr, t_now, t_step_old, h_step);
+                                ybuf = scr;
+                            }
+                        }
+                    }
+                } else {
+                    status = ST_NO_ERROR;
+                }
+            }
             // ---- t_eval emission (cysolver.cpp:838-967) or plain save (:968-972)
             bool do_save = true;
-            if (p.n_t_eval > 0 && !te_finished) {
+            if (p.n_t_eval > 0 && !te_finished && !error_flag) {
                 do_save = false;
                 unsigned lo = 0, hi = p.n_t_eval;
                 while (lo < hi) { const unsigned m = (lo + hi) >> 1; if (p.t_eval[m] < t_now) lo = m + 1; else hi = m; }
@@ -510,8 +680,8 @@ struct Cta2Solver {
                 const bool any = fwd ? (idx_new > te_old) : (te_old > idx_new);
                 const unsigned delta = fwd ? (idx_new - te_old) : (te_old - idx_new);
                 if (any) {
-                    const double h = t_now - t_old;
-                    if (!extra_done) dense_extra_stages();
+                    const double h = h_step;
+                    if (!extra_done) { dense_extra_stages(); if (extra_counted) nfev -= 3; }
                     for (unsigned q = 0; q < delta; q++) {
                         const double ti = fwd ? p.t_eval[te_old + q] : p.t_eval[te_old - q - 1];
                         const double x = (ti - t_old) / h;
@@ -560,18 +730,24 @@ struct Cta2Solver {
             p.nfev[traj] = nfev;
             p.t_last[traj] = t_last;
             if (p.dense_count != nullptr) p.dense_count[traj] = n_dense;
+            if constexpr (EVENTS) {
+                p.ev_term_index[traj] = term_index;
+                for (int e = 0; e < p.n_events; e++) p.ev_count[traj * p.n_events + e] = ev_hits[e];
+            }
         }
     }
 };
 
-template <class Prob, int METHOD, int C>
+template <class Prob, int METHOD, int C, bool EVENTS = false>
 CYRK_DI void rk_cta2_body(const CtaParams& p)
 {
-    using Solver = Cta2Solver<Prob, METHOD, C>;
+    using Solver = Cta2Solver<Prob, METHOD, C, EVENTS>;
     extern __shared__ double smem[];
     __shared__ double red[2][32];
     __shared__ unsigned long long next_traj;
+    __shared__ double ev_vals[1 + CYRK_MAX_EVENTS];
     Solver S;
+    S.gsh = ev_vals;
     S.n = p.n;
     S.T = blockDim.x;
     S.tid = threadIdx.x;
@@ -583,7 +759,9 @@ CYRK_DI void rk_cta2_body(const CtaParams& p)
     S.buf1 = smem + S.V;
     S.aux = smem + 2u * S.V;
     S.ksm = smem + 3u * S.V;
-    S.kgl = p.scratch + (unsigned long long)blockIdx.x * (unsigned long long)(Solver::NGL > 0 ? Solver::NGL : 1) * S.V;
+    // per-CTA global slab: the K vectors that fit neither registers nor shared memory, then one vector for root searches
+    S.kgl = p.scratch + (unsigned long long)blockIdx.x * (unsigned long long)((Solver::NGL > 0 ? Solver::NGL : 1) + 1) * S.V;
+    S.xbuf = S.kgl + (unsigned long long)(Solver::NGL > 0 ? Solver::NGL : 1) * S.V;
     S.uni_tol = p.uniform_tol != 0;
     S.rt0 = p.rtol0;
     S.at0 = p.atol0;
@@ -597,10 +775,10 @@ CYRK_DI void rk_cta2_body(const CtaParams& p)
     }
 }
 
-template <class Prob, int METHOD, int C>
+template <class Prob, int METHOD, int C, bool EVENTS>
 __global__ void __launch_bounds__(cta2_max_block, 1) rk_cta2_kernel(const __grid_constant__ CtaParams p)
 {
-    rk_cta2_body<Prob, METHOD, C>(p);
+    rk_cta2_body<Prob, METHOD, C, EVENTS>(p);
 }
 
 // ------------------------------------------------------------------------------------------------

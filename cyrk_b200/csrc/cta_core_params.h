@@ -38,6 +38,16 @@ struct CtaParams {
     double*   dense_state;       // [n_traj][dense_cap][n * (Q_ORDER + 1)]
     unsigned* dense_count;       // [n_traj]
     unsigned  dense_cap;
+    // ---- events (register-resident kernel only): same records as the thread path (BatchParams)
+    int       n_events;
+    int       ev_id[8];
+    int       ev_dir[8];
+    unsigned long long ev_max[8];         // ~0ull = never terminate
+    double*   ev_t;              // [n_traj][n_events][ev_cap]
+    double*   ev_y;              // [n_traj][n_events][ev_cap][n]
+    unsigned* ev_count;          // [n_traj][n_events]
+    int*      ev_term_index;     // [n_traj]   (-1 = none)
+    unsigned  ev_cap;
     double*   scratch;           // [gridDim.x][n_vec_global + 1][n_pad]: spilled vectors + the problem's aux table
     unsigned  n_smem_vec;        // how many of the working vectors live in shared memory
     unsigned long long* queue;

@@ -2,8 +2,8 @@
 // ONE floating-point mode: compiled twice by the Makefile (-DCYRK_FP_NS=fast -fmad=true / strict -fmad=false).
 #include "cta_core.cuh"
 #include "cta2_core.cuh"
-#include "problems_large.cuh"
 #include "problems_builtin.cuh"
+#include "problems_large.cuh"
 #include "cta_solver.h"
 
 #define CYRK_CAT2_(a, b) a##b
@@ -31,13 +31,18 @@ cudaError_t by_method(int method, const CtaParams& p, int grid, int block, size_
     }
 }
 // register-resident kernels (cta2_core.cuh): C components per thread
+template <class Prob, int METHOD, int C, bool EVENTS>
+cudaError_t go2e(const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(rk_cta2_kernel<Prob, METHOD, C, EVENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rk_cta2_kernel<Prob, METHOD, C, EVENTS><<<grid, block, smem, s>>>(p);
+    return cudaGetLastError();
+}
 template <class Prob, int METHOD, int C>
 cudaError_t go2(const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
 {
-    cudaError_t e = cudaFuncSetAttribute(rk_cta2_kernel<Prob, METHOD, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    rk_cta2_kernel<Prob, METHOD, C><<<grid, block, smem, s>>>(p);
-    return cudaGetLastError();
+    return p.n_events > 0 ? go2e<Prob, METHOD, C, true>(p, grid, block, smem, s) : go2e<Prob, METHOD, C, false>(p, grid, block, smem, s);
 }
 template <class Prob, int METHOD>
 cudaError_t by_c(int C, const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)

@@ -19,6 +19,8 @@ cudaError_t user_rhs_launch_dense(int rhs_id, int method, bool strict, int devic
                                   cudaStream_t s);
 // Large systems (registered with n_y == 0): the source defines
 //     __device__ double <entry>(unsigned i, double t, const double* y, unsigned n, const char* args);   -> dy_i
+// and, when registered with n_events > 0,
+//     __device__ double <entry>_event(int id, double t, const double* y, unsigned n, const char* args); -> g_id(t, y)
 // cta2_C > 0: the register-resident kernel (cta2_core.cuh) with that many components per thread; 0: cta_core.cuh
 cudaError_t user_rhs_launch_cta(int rhs_id, int method, int cta2_C, bool strict, int device, const CtaParams& p, int grid, int block,
                                 size_t smem, cudaStream_t s);

@@ -21,6 +21,11 @@ struct ProbLargeY {
         }
         __syncthreads();
     }
+    // events: the flat built-in table (they read y[0], y[1], y[2], t only; problems_builtin.cuh)
+    __device__ __forceinline__ static double event(int id, double t, const double* y, unsigned, const char* args)
+    {
+        return builtin_event<3, 2>(id, t, y, args);
+    }
     __device__ __forceinline__ static double eval(unsigned i, double t, const double* y, unsigned n, const char*, const double* aux)
     {
         const double pi = 3.14159265358979323846;
@@ -39,6 +44,10 @@ struct ProbLargeY {
 struct ProbLargeYSimple {
     static constexpr bool INLINE_EVAL = true;
     __device__ __forceinline__ static void prepare(const char*, unsigned, double*, bool) { __syncthreads(); }
+    __device__ __forceinline__ static double event(int id, double t, const double* y, unsigned, const char* args)
+    {
+        return builtin_event<3, 2>(id, t, y, args);
+    }
     __device__ __forceinline__ static double eval(unsigned i, double t, const double*, unsigned, const char*, const double*)
     {
         const double pi = 3.14159265358979323846;

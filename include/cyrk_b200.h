@@ -52,7 +52,7 @@ extern "C" {
 #define CYRK_RHS_PENDULUM          6
 #define CYRK_RHS_ARBITRARY_ARGS    7
 #define CYRK_RHS_PENDULUM_PREEVAL  8
-#define CYRK_RHS_LARGEY            9   /* CTA-per-trajectory path, any n_y */
+#define CYRK_RHS_LARGEY            9   /* CTA-per-trajectory path, any n_y (events / dense output: n_y <= 4096) */
 #define CYRK_RHS_LARGEY_SIMPLE     10  /* CTA-per-trajectory path, any n_y */
 #define CYRK_RHS_PENDULUM_DRAG     11
 #define CYRK_RHS_DENSE_KAT         12
@@ -99,7 +99,11 @@ int cyrk_b200_rhs_info(int rhs_id, size_t* n_y, size_t* n_extra, size_t* args_by
  * and, when n_event_funcs > 0,
  *     __device__ double <entry>_event(int id, double t, const double* y_and_extras, const char* args);
  * mirroring DiffeqFuncType / EventFunc (c_common.hpp:218-220, c_events.hpp:9); a pre-eval hook is
- * just another __device__ function the source calls.  Returns an id >= CYRK_RHS_USER_BASE, or -1
+ * just another __device__ function the source calls.  LARGE systems (n_y == 0 here; the size comes with each solve
+ * call; CTA-per-trajectory path, no extra outputs) are written component-wise instead:
+ *     __device__ double <entry>(unsigned i, double t, const double* y, unsigned n, const char* args);      -> dy_i
+ *     __device__ double <entry>_event(int id, double t, const double* y, unsigned n, const char* args);     -> g_id
+ * Returns an id >= CYRK_RHS_USER_BASE, or -1
  * (compile log in `log`).  Compiled modules are cached by source hash for the process lifetime. */
 int cyrk_b200_rhs_compile(const char* source, const char* entry, size_t n_y, size_t n_extra,
                           size_t args_bytes, size_t n_event_funcs, char* log, size_t log_len);

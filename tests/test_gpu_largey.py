@@ -70,10 +70,13 @@ def test_largey_simple_and_unsupported_features():
     assert (r.status == 1).all()
     # dy_0 = sin(2 pi t / 10), the rest is constant: y_0(10) = 100 + (10/2pi)(1 - cos(2 pi)) = 100
     assert np.allclose(r.y_last[:, 0], 100.0, atol=5e-3) and np.all(r.y_last[:, 1:] == 100.0)
+    with pytest.raises(c.CyrkB200Error):        # no extra outputs on the CTA path
+        c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, args=[-0.5, float(n)], num_extra=1)
+    big = 100.0 * np.ones((2, 5000))            # stored dense output / events need the register-resident kernel (n_y <= 4096)
     with pytest.raises(c.CyrkB200Error):
-        c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, args=[-0.5, float(n)], events=[c.Event("y0")])
-    with pytest.raises(c.CyrkB200Error):        # stored dense output needs the register-resident kernel (n_y <= 4096)
-        c.cysolve_ivp_batch("largey", (0.0, 10.0), 100.0 * np.ones((2, 5000)), args=[-0.5, 5000.0], dense_output=True)
+        c.cysolve_ivp_batch("largey", (0.0, 10.0), big, args=[-0.5, 5000.0], dense_output=True)
+    with pytest.raises(c.CyrkB200Error):
+        c.cysolve_ivp_batch("largey", (0.0, 10.0), big, args=[-0.5, 5000.0], events=[c.Event("y0")])
 
 
 @pytest.mark.parametrize("n", [700, 1500, 3000, 5000])
@@ -208,3 +211,42 @@ def test_cta_failure_statuses_match_oracle(oracle):
             assert (r.status == -80).all() and (r.steps_taken == 0).all()
         finally:
             c.lib().cyrk_b200_set_option(b"cta_kernel", 0)
+
+
+@pytest.mark.parametrize("method", ["RK23", "RK45", "DOP853"])
+@pytest.mark.parametrize("n", [130, 1500])
+def test_cta_events_match_oracle(oracle, method, n):
+    """Events on the CTA path (register-resident kernel): the reference's built-in event functions on largey --
+    step functions, so every search runs the reference's special cases (f(xa) == 0, f(xb) == 0, bisection on a
+    discontinuity) --, non-terminal and terminal, with t_eval and stored dense output, vs the oracle."""
+    rng = np.random.default_rng(51)
+    B = 3
+    y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (B, n)))
+    args = [-0.5, float(n)]
+    cases = [
+        ([("y0_gt_50", 0, None), ("y1_lt_50", 0, None), ("t_gt_5", 0, None)], None, False),
+        ([("t_gt_5", 0, 1)], None, False),                                   # terminal: ends inside a step
+        ([("y1_lt_50", 0, None), ("t_gt_5", 0, 3)], np.linspace(0.0, 10.0, 7), True),
+        ([("t_gt_5", -1, None), ("t_gt_5", 1, None)], None, False),          # direction filters
+    ]
+    for evs, t_eval, dense in cases:
+        events = [c.Event(name, direction=d, max_allowed=m) for (name, d, m) in evs]
+        r = c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method=method, args=args, rtol=1e-6, atol=1e-8, events=events,
+                                t_eval=t_eval, dense_output=dense, expected_size=2)     # tiny capacities: exact re-run
+        for i in (0, B - 1):
+            ref = oracle.solve("largey", (0.0, 10.0), y0[i], method, 1e-6, 1e-8, args=args, events=evs, t_eval=t_eval,
+                               dense_output=dense)
+            v = r[i]
+            assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken), (method, n, evs)
+            assert int(r.nfev[i]) == ref.nfev
+            assert [len(t) for t in v.t_events] == [len(t) for t in ref.t_events]
+            for a, b in zip(v.t_events, ref.t_events):
+                assert np.allclose(a, b, rtol=1e-6, atol=1e-9)
+            for a, b in zip(v.y_events, ref.y_events):
+                assert a.shape == b.shape and np.all(np.abs(a - b) <= _tol(b, 1e-6, 1e-8))
+            assert v.event_terminated == ref.event_terminated
+            if ref.event_terminated:
+                assert v.event_terminate_index == ref.event_terminate_index
+            assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
+            assert np.all(np.abs(v.y - ref.y) <= _tol(ref.y, 1e-6, 1e-8))
+        r.close()

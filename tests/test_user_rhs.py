@@ -139,3 +139,51 @@ def test_large_user_rhs_matches_oracle(oracle, method, n):
             assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken)
             assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
             assert np.all(np.abs(v.y - ref.y) <= 10 * 1e-6 * np.abs(ref.y) + 10 * 1e-9)
+
+
+CHAIN_EV_SRC = CHAIN_SRC + r'''
+// events of a large user system: g(id, t, y[n], n, args)
+__device__ double chain_event(int id, double t, const double* y, unsigned n, const char* args) {
+    if (id == 0) return y[0];
+    if (id == 1) return y[1];
+    return (t > 5.0) ? 0.0 : 1.0;
+}
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["RK45", "DOP853"])
+def test_large_user_rhs_with_events(oracle, method):
+    """Large user system (NVRTC, CTA path) with user event functions: zero crossings of y[0] (any direction) and y[1]
+    (falling), and a terminal step-function event at t = 5; vs the oracle with the same right-hand side as a callback and
+    the built-in events of the same meaning."""
+    import ctypes as C
+    n, B = 200, 3
+    u = c.UserRHS(CHAIN_EV_SRC, "chain", n_y=0, args_bytes=8, n_events=3)
+    rng = np.random.default_rng(19)
+    y0 = rng.uniform(-0.5, 0.5, (B, n))
+    rates = np.array([[0.5], [0.8], [1.1]])
+
+    @oracle.DIFFEQ_FN
+    def chain_cb(dy, t, y, args, pre):
+        yy = np.ctypeslib.as_array(y, shape=(n,))
+        r = C.cast(args, C.POINTER(C.c_double))[0]
+        left = np.concatenate([[0.0], yy[:-1]])
+        right = np.concatenate([yy[1:], [0.0]])
+        out = r * (left - 2.0 * yy + right) + 0.1 * np.sin(t)
+        C.memmove(dy, out.ctypes.data, 8 * n)
+
+    ev = [c.Event(0), c.Event(1, direction=-1), c.Event(2, terminal=True)]
+    r = c.cysolve_ivp_batch(u, (0.0, 8.0), y0, method=method, args=rates, rtol=1e-6, atol=1e-9, events=ev)
+    for i in range(B):
+        ref = oracle.solve(chain_cb, (0.0, 8.0), y0[i], method, 1e-6, 1e-9, args=rates[i], num_extra=0,
+                           events=[("y0", 0, None), ("y1", -1, None), ("t_gt_5", 0, 1)])
+        v = r[i]
+        assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken) and v.status == 2
+        assert [len(t) for t in v.t_events] == [len(t) for t in ref.t_events]
+        for a, b in zip(v.t_events, ref.t_events):
+            assert np.allclose(a, b, rtol=1e-6, atol=1e-9)
+        for a, b in zip(v.y_events, ref.y_events):
+            assert np.all(np.abs(a - b) <= 10 * 1e-6 * np.abs(b) + 10 * 1e-9)
+        assert v.event_terminate_index == ref.event_terminate_index == 2
+        assert np.all(np.abs(v.y - ref.y) <= 10 * 1e-6 * np.abs(ref.y) + 10 * 1e-9)
