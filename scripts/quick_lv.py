@@ -9,6 +9,8 @@ import torch
 y0 = torch.from_numpy(np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)).cuda()
 args_d = torch.tensor([1.5, 1, 3, 1], dtype=torch.float64, device='cuda'); ts_d = torch.tensor([0., 10.], dtype=torch.float64, device='cuda')
 cfgs = [(1, 1, 128)] if not os.environ.get("SWEEP") else [(1, r, b) for r in (1, 2, 3, 4, 6) for b in (128, 256)]
+if os.environ.get("SWEEP") == "prep":
+    cfgs = [(pr, r, 128) for pr in (0, 1) for r in (1, 2, 4)]
 for prep, refill, block in cfgs:
     c.lib().cyrk_b200_set_option(b'block', block)
     c.lib().cyrk_b200_set_option(b"refill_min", refill)
