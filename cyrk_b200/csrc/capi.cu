@@ -15,6 +15,7 @@
 #include <limits>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/cyrk_b200.h"
@@ -1214,6 +1215,51 @@ void* cyrk_b200_solve_batch(
         return nullptr;
     }
     return h;
+}
+
+int cyrk_b200_solve_batch_sharded(
+    const int* device_ids, size_t n_dev, void** handles_out, size_t* bounds_out,
+    int rhs_id, int method, size_t n_traj, const double* t_span, size_t n_t_span, const double* y0, size_t n_y,
+    size_t num_extra, const char* args, size_t args_len, size_t n_args, size_t max_num_steps, size_t max_ram_MB,
+    int dense_output, const double* t_eval, size_t n_t_eval, const int* event_ids, const int* event_dirs,
+    const size_t* event_max, size_t n_events, const double* rtols, size_t n_rtols, const double* atols, size_t n_atols,
+    double max_step, double first_step, size_t expected_size, int store_mode, unsigned flags)
+{
+    if (!device_ids || !handles_out || n_dev == 0) { set_error("device_ids, handles_out and n_dev > 0 are required"); return -1; }
+    if (flags & CYRK_FLAG_DEVICE_IO) { set_error("the sharded call takes host buffers (each shard is copied to its own device)"); return -1; }
+    if (n_traj < n_dev) { set_error("fewer trajectories (%zu) than devices (%zu)", n_traj, n_dev); return -1; }
+    // contiguous shards; the first n_traj % n_dev get one extra (== cyrk_b200.sharding.shard_bounds)
+    std::vector<size_t> lo(n_dev + 1, 0);
+    for (size_t r = 0; r < n_dev; r++) lo[r + 1] = lo[r] + n_traj / n_dev + (r < n_traj % n_dev ? 1 : 0);
+    std::vector<Handle*> hs(n_dev, nullptr);
+    std::vector<int> rc(n_dev, 0);
+    std::vector<std::string> err(n_dev);
+    std::vector<std::thread> th;
+    const bool per_span = n_t_span > 1, per_args = n_args > 1;
+    for (size_t r = 0; r < n_dev; r++) {
+        hs[r] = new Handle();
+        th.emplace_back([&, r]() {
+            const size_t o = lo[r], n = lo[r + 1] - lo[r];
+            SolveArgs a{rhs_id, method, n, per_span ? t_span + 2 * o : t_span, per_span ? n : n_t_span, y0 + o * n_y, n_y,
+                        num_extra, per_args ? args + o * args_len : args, args_len, per_args ? n : n_args, max_num_steps,
+                        max_ram_MB, dense_output, t_eval, n_t_eval, event_ids, event_dirs, event_max, n_events, rtols,
+                        n_rtols, atols, n_atols, max_step, first_step, expected_size, store_mode, flags, device_ids[r]};
+            rc[r] = solve_impl(hs[r], a);
+            if (rc[r]) err[r] = g_last_error;          // thread-local: carry it to the caller's thread
+        });
+    }
+    for (auto& t : th) t.join();
+    for (size_t r = 0; r < n_dev; r++) {
+        if (rc[r]) {
+            const std::string msg = err[r];
+            for (size_t k = 0; k < n_dev; k++) delete hs[k];
+            set_error("shard %zu (device %d): %s", r, device_ids[r], msg.c_str());
+            return -1;
+        }
+    }
+    for (size_t r = 0; r < n_dev; r++) handles_out[r] = hs[r];
+    if (bounds_out) for (size_t r = 0; r <= n_dev; r++) bounds_out[r] = lo[r];
+    return 0;
 }
 
 #define H(h) (static_cast<Handle*>(h))

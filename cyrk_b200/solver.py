@@ -317,6 +317,7 @@ def cysolve_ivp_batch(
         strict_fp: bool = False,
         device: int = 0,
         solution_reuse: Optional[BatchResult] = None,
+        devices: Optional[Sequence[int]] = None,
 ) -> BatchResult:
     """Solve ``B`` independent initial-value problems on one B200.
 
@@ -327,6 +328,9 @@ def cysolve_ivp_batch(
       store     'rows'  -> every row the reference would save (``result[i].t/.y``)
                 'final' -> only the last row and the counters (``result.y_last``)
       strict_fp run the -fmad=false kernels (the reference's rounding: no FMA contraction)
+      devices   several CUDA ordinals: the batch is cut into contiguous shards, one per device, solved concurrently by
+                the native library (one host thread + stream per device, no communication); the call then returns
+                a list of ``(lo, hi, BatchResult)`` -- shard r holds the trajectories ``[lo, hi)``
     """
     L = _lib.lib()
     method_int = find_ode_method_int(method)
@@ -429,6 +433,16 @@ def cysolve_ivp_batch(
         float(max_step), float(first_step),
         int(expected_size),
         store_mode, flags, int(device))
+    if devices is not None and len(devices) > 0:
+        if device_io or solution_reuse is not None:
+            raise ValueError("devices=[...] takes host arrays and fresh result handles")
+        nd = len(devices)
+        dev = (C.c_int * nd)(*[int(d) for d in devices])
+        hs = (C.c_void_p * nd)()
+        bounds = (C.c_size_t * (nd + 1))()
+        if L.cyrk_b200_solve_batch_sharded(dev, nd, hs, bounds, *call_args[:-1]) != 0:
+            raise CyrkB200Error(_lib.last_error())
+        return [(int(bounds[r]), int(bounds[r + 1]), BatchResult(hs[r], method_int, keep_inputs=keep)) for r in range(nd)]
     if solution_reuse is not None:
         # CySolverResult reuse (Documentation/CySolverResult_Reuses.md): same arena, new problem
         h = solution_reuse._h

@@ -146,6 +146,28 @@ void* cyrk_b200_solve_batch(
     size_t expected_size,
     int store_mode, unsigned flags, int device);
 
+/* The same call over several GPUs of ONE process (Documentation/Parallelization.md: trajectories are independent):
+ * contiguous shards, one host thread and one stream per device, no communication.  Shard r owns the trajectories
+ * [bounds_out[r], bounds_out[r+1]) (the first n_traj % n_dev shards get one extra) and comes back as its own handle in
+ * handles_out[r]; per-trajectory inputs (y0, per-trajectory t_span / args) are sliced accordingly.  Host buffers only.
+ * Returns 0, or -1 (no handle is left allocated).  The one-process-per-GPU alternative is bench.py / torchrun. */
+int cyrk_b200_solve_batch_sharded(
+    const int* device_ids, size_t n_dev, void** handles_out, size_t* bounds_out /* [n_dev + 1] or NULL */,
+    int rhs_id, int method, size_t n_traj,
+    const double* t_span, size_t n_t_span,
+    const double* y0, size_t n_y,
+    size_t num_extra,
+    const char* args, size_t args_len, size_t n_args,
+    size_t max_num_steps, size_t max_ram_MB,
+    int dense_output,
+    const double* t_eval, size_t n_t_eval,
+    const int* event_ids, const int* event_dirs, const size_t* event_max, size_t n_events,
+    const double* rtols, size_t n_rtols,
+    const double* atols, size_t n_atols,
+    double max_step, double first_step,
+    size_t expected_size,
+    int store_mode, unsigned flags);
+
 /* Same, re-using the device arena / pinned host buffers of an existing handle
  * (cysolve_ivp_noreturn / solution_reuse, CyRK/cy/cysolve.cpp:6-59).  Returns 0 or -1. */
 int cyrk_b200_solve_batch_noreturn(

@@ -42,6 +42,15 @@ cdef extern from "cyrk_b200.h" nogil:
     int cyrk_b200_rhs_info(int rhs_id, size_t* n_y, size_t* n_extra, size_t* args_bytes)
     int cyrk_b200_rhs_compile(const char* source, const char* entry, size_t n_y, size_t n_extra, size_t args_bytes, size_t n_event_funcs, char* log, size_t log_len)
     void* cyrk_b200_solve_batch( int rhs_id, int method, size_t n_traj, const double* t_span, size_t n_t_span, const double* y0, size_t n_y, size_t num_extra, const char* args, size_t args_len, size_t n_args, size_t max_num_steps, size_t max_ram_MB, int dense_output, const double* t_eval, size_t n_t_eval, const int* event_ids, const int* event_dirs, const size_t* event_max, size_t n_events, const double* rtols, size_t n_rtols, const double* atols, size_t n_atols, double max_step, double first_step, size_t expected_size, int store_mode, unsigned int flags, int device)
+    int cyrk_b200_solve_batch_sharded(const int* device_ids, size_t n_dev, void** handles_out, size_t* bounds_out,
+                                int rhs_id, int method, size_t n_traj,
+                                const double* t_span, size_t n_t_span, const double* y0, size_t n_y, size_t num_extra,
+                                const char* args, size_t args_len, size_t n_args, size_t max_num_steps, size_t max_ram_MB,
+                                int dense_output, const double* t_eval, size_t n_t_eval,
+                                const int* event_ids, const int* event_dirs, const size_t* event_max, size_t n_events,
+                                const double* rtols, size_t n_rtols, const double* atols, size_t n_atols,
+                                double max_step, double first_step, size_t expected_size,
+                                int store_mode, unsigned int flags)
     int cyrk_b200_solve_batch_noreturn( void* handle, int rhs_id, int method, size_t n_traj, const double* t_span, size_t n_t_span, const double* y0, size_t n_y, size_t num_extra, const char* args, size_t args_len, size_t n_args, size_t max_num_steps, size_t max_ram_MB, int dense_output, const double* t_eval, size_t n_t_eval, const int* event_ids, const int* event_dirs, const size_t* event_max, size_t n_events, const double* rtols, size_t n_rtols, const double* atols, size_t n_atols, double max_step, double first_step, size_t expected_size, int store_mode, unsigned int flags, int device)
     void* cyrk_b200_result_create()
     void cyrk_b200_free(void* handle)

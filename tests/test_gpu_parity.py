@@ -415,3 +415,28 @@ def test_full_size_c3_properties():
     # step statistics: SURVEY 8d probe (undamped) mean 1480; the damped variant needs fewer
     full = ~stopped
     assert 500 < r.steps_taken[full].mean() < 1800
+
+
+def test_native_sharded_solve_over_device_list():
+    """cyrk_b200_solve_batch_sharded (devices=[...]): contiguous shards solved concurrently by native host threads.
+    With one GPU visible both shards go to device 0 (distinct handles, concurrent calls: the thread-safety contract);
+    results must equal the single-call solve bit for bit, including per-trajectory args and spans."""
+    rng = np.random.default_rng(7)
+    B = 10001                                        # not divisible: the first two shards get one extra trajectory
+    y0 = np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)
+    args = np.stack([rng.uniform(1.4, 1.6, B), np.ones(B), np.full(B, 3.0), np.ones(B)], 1)
+    spans = np.stack([np.zeros(B), rng.uniform(5.0, 10.0, B)], 1)
+    ndev = c.lib().cyrk_b200_device_count()
+    devices = [0, 1 % ndev, 0]
+    kw = dict(method="RK45", args=args, rtol=1e-7, atol=1e-9, store="rows", expected_size=300)
+    whole = c.cysolve_ivp_batch("lotkavolterra", spans, y0, **kw)
+    shards = c.cysolve_ivp_batch("lotkavolterra", spans, y0, devices=devices, **kw)
+    from cyrk_b200.sharding import shard_bounds
+    assert [(lo, hi) for lo, hi, _ in shards] == [shard_bounds(B, r, 3) for r in range(3)] == [(0, 3334), (3334, 6668), (6668, B)]
+    for lo, hi, r in shards:
+        assert r.n_traj == hi - lo
+        assert np.array_equal(r.status, whole.status[lo:hi]) and np.array_equal(r.steps_taken, whole.steps_taken[lo:hi])
+        assert np.array_equal(r.y_last, whole.y_last[lo:hi]) and np.array_equal(r.t_last, whole.t_last[lo:hi])
+        assert np.array_equal(r[0].y, whole[lo].y) and np.array_equal(r[hi - lo - 1].t, whole[hi - 1].t)
+    with pytest.raises(c.CyrkB200Error):
+        c.cysolve_ivp_batch("lotkavolterra", spans, y0, devices=[0, 99], **kw)       # bad ordinal: nothing leaks, error names the shard
