@@ -181,10 +181,33 @@ def run_reference_arm(a, w, rank, world):
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner with a plain
+    printf whenever NCCL_DEBUG is VERSION or WARN, which NCCL_DEBUG_FILE does not redirect), so file descriptor 1 is
+    pointed at stderr for the whole run and the JSON line goes to a private duplicate of the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -218,10 +241,6 @@ def main():
         from cyrk_b200.sharding import bind_to_device_numa
         numa_cores = bind_to_device_numa(local_rank)
     if world > 1:
-        # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION (this image's default): keep stdout to the
-        # one JSON line the contract asks for
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -346,7 +365,7 @@ def main():
                                     "kind": r["kind"],
                                     "sample": f"{r['n']} trajectories of the same generator (seed 12345), "
                                               f"{r['seconds']:.1f} s on {r['threads']} host threads"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
