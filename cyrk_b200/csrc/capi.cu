@@ -91,7 +91,8 @@ static int g_opt_cta_smem_vecs = -1;  // CTA path: working vectors kept in share
 static int g_opt_cta_block = 0;       // CTA path: threads per CTA (0 = by n_y)
 static int g_opt_pipe_taper = 1;       // pipelined host-I/O path: short first / last chunks
 static int g_opt_pipe_chunk = 1 << 20; // pipelined host-I/O path: trajectories per chunk (at most 32 chunks)
-static int g_opt_cta_kernel = 0;      // CTA path: 0 = register-resident kernel where it applies, 1 = always the shared-memory/slab kernel
+static int g_opt_cta_kernel = 0;      // CTA path: 0 = pick (register-resident kernel where it is faster), 1 = always the
+                                      // shared-memory/slab kernel, 2 = the register-resident kernel whenever n_y <= 4096
 static int g_opt_root_batch = 12;     // measured: 8..16 is the flat optimum on the C3 workload (profiles/r01_notes.md)
 static int g_opt_ctas_per_sm = 0;
 
@@ -799,7 +800,12 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     CU_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     int smem_per_sm = 0;
     CU_TRY(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
-    const bool use_cta2 = g_opt_cta_kernel != 1 && N <= (size_t)8 * cta2_max_block;
+    // Measured at n_y = 4096 (scripts/quick_c4_methods.py): the register-resident kernel wins for RK23 (16.7 vs 20.0 ms)
+    // and RK45 (5.3 vs 5.7 ms; 2.3x with a cheap right-hand side), but with DOP853's 16 stage vectors and 8 components per
+    // thread it spills (7.9 vs 6.1 ms): that one case stays on the shared-memory/slab kernel unless a feature only the
+    // register-resident kernel has (stored dense output, events) is requested.
+    const bool dop_c8 = a.method == CYRK_METHOD_DOP853 && N > (size_t)4 * cta2_max_block && !a.dense_output && a.n_events == 0;
+    const bool use_cta2 = g_opt_cta_kernel != 1 && N <= (size_t)8 * cta2_max_block && !(dop_c8 && g_opt_cta_kernel == 0);
     int cta2_C = 0;
     int block, grid;
     size_t smem;
