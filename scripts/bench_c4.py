@@ -12,6 +12,7 @@ y0d = torch.from_numpy(y0).cuda()
 ts = torch.tensor([0.0, 10.0], dtype=torch.float64, device="cuda")
 ar = torch.tensor([-0.5, float(n)], dtype=torch.float64, device="cuda")
 import itertools
+KERNEL = int(os.environ.get("CTA_KERNEL", 0)); c.lib().cyrk_b200_set_option(b"cta_kernel", KERNEL)
 cfgs = [(-1, 0)] + [(v, b) for v in (9, 7, 4, 3, 2, 0) for b in (1024, 512)] if os.environ.get("SWEEP") else [(-1, 0)]
 for (sv, blk), rhs in itertools.product(cfgs, ("largey", "largey_simple")):
     c.lib().cyrk_b200_set_option(b"cta_smem_vecs", sv); c.lib().cyrk_b200_set_option(b"cta_block", blk)
