@@ -93,6 +93,7 @@ static int g_opt_pipe_taper = 1;       // pipelined host-I/O path: short first /
 static int g_opt_pipe_chunk = 1 << 20; // pipelined host-I/O path: trajectories per chunk (at most 32 chunks)
 static int g_opt_cta_kernel = 0;      // CTA path: 0 = pick (register-resident kernel where it is faster), 1 = always the
                                       // shared-memory/slab kernel, 2 = the register-resident kernel whenever n_y <= 4096
+static int g_opt_two_pass = 1;        // t_eval / dense_output without events or extras: step-parallel interpolants (0 = the one-pass kernel)
 static int g_opt_root_batch = 12;     // measured: 8..16 is the flat optimum on the C3 workload (profiles/r01_notes.md)
 static int g_opt_ctas_per_sm = 0;
 
@@ -166,6 +167,7 @@ struct Handle {
     DevBuf d_trows, d_yrows, d_dense_t, d_dense_state, d_dense_count;
     DevBuf d_ev_t, d_ev_y, d_ev_count, d_ev_term;
     DevBuf d_q_t, d_q_out, d_q_code, d_scratch, d_prep, d_rtol, d_atol;
+    DevBuf d_st_t, d_st_h, d_st_y;          // step records of the two-pass t_eval / dense path
     // pinned host mirrors
     PinBuf h_status, h_size, h_steps, h_nrej, h_nfev, h_tlast, h_ylast;
     PinBuf h_trows, h_yrows, h_dense_count, h_ev_t, h_ev_y, h_ev_count, h_ev_term;
@@ -201,7 +203,8 @@ struct Handle {
         if (device >= 0) cudaSetDevice(device);
         DevBuf* dbs[] = {&d_y0, &d_args, &d_tspan, &d_teval, &d_queue, &d_status, &d_size, &d_steps, &d_nrej, &d_nfev,
                          &d_tlast, &d_ylast, &d_trows, &d_yrows, &d_dense_t, &d_dense_state, &d_dense_count, &d_ev_t,
-                         &d_ev_y, &d_ev_count, &d_ev_term, &d_q_t, &d_q_out, &d_q_code, &d_scratch, &d_prep, &d_rtol, &d_atol};
+                         &d_ev_y, &d_ev_count, &d_ev_term, &d_q_t, &d_q_out, &d_q_code, &d_scratch, &d_prep, &d_rtol, &d_atol,
+                         &d_st_t, &d_st_h, &d_st_y};
         for (DevBuf* b : dbs) b->release();
         PinBuf* pbs[] = {&h_status, &h_size, &h_steps, &h_nrej, &h_nfev, &h_tlast, &h_ylast, &h_trows, &h_yrows,
                          &h_dense_count, &h_ev_t, &h_ev_y, &h_ev_count, &h_ev_term, &h_stage};
@@ -254,6 +257,11 @@ struct Dispatch {
     {
         if (pe) return pe->prep[method - 3](p, out, grid, block, s);
         return user_rhs_launch_prep(rhs_id, method, strict, device, p, out, grid, block, s);
+    }
+    cudaError_t step_dense(int method, const StepDenseParams& p, int grid, int block, cudaStream_t s) const
+    {
+        if (pe) return pe->step_dense[method - 3](p, grid, block, s);
+        return user_rhs_launch_step_dense(rhs_id, method, strict, device, p, grid, block, s);
     }
     cudaError_t dense(int method, const DenseEvalParams& p, int grid, int block, cudaStream_t s) const
     {
@@ -462,6 +470,42 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
 }
 
 // The thread-per-trajectory path.  Returns 0 / -1.
+// Last pass of the step-parallel t_eval path: rows saved (= position of the t_eval cursor after the last booked step,
+// cysolver.cpp:848-878) and the last saved row, per trajectory.
+__global__ void teval_last_kernel(unsigned long long n_traj, const unsigned* __restrict__ steps, const double* __restrict__ t_steps,
+                                  unsigned step_cap, const double* __restrict__ t_span, unsigned t_span_stride,
+                                  const double* __restrict__ t_eval, unsigned n_t_eval, const double* __restrict__ t_rows,
+                                  const double* __restrict__ y_rows, unsigned row_cap, unsigned ndy, unsigned* __restrict__ size,
+                                  double* __restrict__ t_last, double* __restrict__ y_last)
+{
+    const unsigned long long traj = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (traj >= n_traj) return;
+    const unsigned ns = steps[traj];
+    const double* ts = t_span + traj * t_span_stride;
+    const bool fwd = (ts[1] - ts[0]) >= 0.0;
+    unsigned sz = 0;
+    if (ns > 0) {
+        const double x = t_steps[traj * step_cap + ns];
+        unsigned a = 0, b = n_t_eval;
+        while (a < b) {
+            const unsigned m = (a + b) >> 1;
+            const double v = t_eval[m];
+            if (fwd ? !(x < v) : (v < x)) a = m + 1; else b = m;
+        }
+        sz = fwd ? a : n_t_eval - a;
+    }
+    size[traj] = sz;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (sz > 0 && sz <= row_cap) {
+        const unsigned long long r = traj * row_cap + (sz - 1);
+        t_last[traj] = t_rows[r];
+        for (unsigned i = 0; i < ndy; i++) y_last[traj * ndy + i] = y_rows[r * ndy + i];
+    } else {
+        t_last[traj] = nan;
+        for (unsigned i = 0; i < ndy; i++) y_last[traj * ndy + i] = nan;
+    }
+}
+
 static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
 {
     const size_t B = a.n_traj, NY = pe->ny, NX = pe->nextra, NDY = NY + NX;
@@ -470,6 +514,26 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     const bool dense = a.dense_output != 0;
     const int variant = a.n_events > 0 ? VAR_FULL : ((dense || want_rows || a.n_t_eval > 0) ? VAR_ROWS : VAR_LEAN);
     const int q_order = a.method == CYRK_METHOD_RK23 ? 3 : a.method == CYRK_METHOD_RK45 ? 4 : 7;
+
+    // Step-parallel interpolants (rk_core.cuh, step_dense_body): a final-state solve that records its booked steps, then one
+    // thread per (trajectory, step).  Taken when the interpolant is only needed for output (no events), the right-hand side has
+    // no extra outputs (those change how the reference rolls its state inside the t_eval loop, cysolver.cpp:915-961), and t_eval
+    // cannot be exhausted before the last step (afterwards the reference saves raw steps again).
+    // Measured (profiles/r01_notes.md): worth it when the interpolants are STORED (dense_output); for t_eval alone the
+    // per-trajectory kernel is as fast and needs no per-step records (option two_pass = 2 forces it there as well).
+    bool two_pass = g_opt_two_pass != 0 && variant == VAR_ROWS && NX == 0 && (dense || (a.n_t_eval > 0 && g_opt_two_pass == 2)) &&
+                    (a.n_t_eval == 0 || want_rows);
+    if (two_pass && a.n_t_eval > 0) {
+        if (a.n_t_span > 1) two_pass = false;
+        else {
+            double ts0[2];
+            if (device_io) {
+                if (cudaMemcpy(ts0, a.t_span, sizeof(ts0), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); set_error("cannot read t_span from the device"); return -1; }
+            } else { ts0[0] = a.t_span[0]; ts0[1] = a.t_span[1]; }
+            const double last = a.t_eval[a.n_t_eval - 1];         // t_eval arrives in the order the run passes it
+            two_pass = ((ts0[1] - ts0[0]) >= 0.0) ? (last >= ts0[1]) : (last <= ts0[1]);
+        }
+    }
 
     h->ny = NY; h->nx = NX; h->ndy = NDY; h->q_order = q_order;
     h->n_traj = B; h->n_events = a.n_events; h->n_t_eval = a.n_t_eval;
@@ -523,26 +587,29 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     // CTA size: 128 threads unless 96 keeps more warps resident (register-heavy variants: Lorenz/DOP853 with rows + dense
     // needs 186 registers -> 2 x 128 or 3 x 96 threads per SM; measured 5.31 vs 4.92 ms on the C2 t_eval+dense workload,
     // while 64-thread CTAs, although they fit 10 warps, were no faster than 128).
-    int grid = 0, block = g_opt_block > 0 ? g_opt_block : 128;
-    {
+    int grid = 0, block = 0;
+    auto pick_grid = [&](int solve_variant) -> int {
+        block = g_opt_block > 0 ? g_opt_block : 128;
         int ctas = 0;
-        if (pe->occupancy(a.method, variant, &ctas, block) != cudaSuccess) {
-            if (g_last_error.empty()) set_error("occupancy query failed for %s", pe->name(a.method, variant));
+        if (pe->occupancy(a.method, solve_variant, &ctas, block) != cudaSuccess) {
+            if (g_last_error.empty()) set_error("occupancy query failed for %s", pe->name(a.method, solve_variant));
             cudaGetLastError();
             return -1;
         }
         if (g_opt_block <= 0) {
             int ctas96 = 0;
-            if (pe->occupancy(a.method, variant, &ctas96, 96) == cudaSuccess && ctas96 * 96 > ctas * 128) { block = 96; ctas = ctas96; }
+            if (pe->occupancy(a.method, solve_variant, &ctas96, 96) == cudaSuccess && ctas96 * 96 > ctas * 128) { block = 96; ctas = ctas96; }
             else cudaGetLastError();
         }
         if (g_opt_ctas_per_sm > 0) ctas = g_opt_ctas_per_sm;
-        if (ctas <= 0) { set_error("kernel %s cannot be resident with %d threads per CTA", pe->name(a.method, variant), block); return -1; }
+        if (ctas <= 0) { set_error("kernel %s cannot be resident with %d threads per CTA", pe->name(a.method, solve_variant), block); return -1; }
         grid = device_sm_count(h->device) * ctas;
         const unsigned long long need = (B + block - 1) / block;
         if ((unsigned long long)grid > need) grid = (int)std::max<unsigned long long>(need, 1);
-        if (getenv("CYRK_B200_DEBUG")) fprintf(stderr, "[cyrk_b200] %s: block %d, %d CTAs/SM, grid %d\n", pe->name(a.method, variant), block, ctas, grid);
-    }
+        if (getenv("CYRK_B200_DEBUG")) fprintf(stderr, "[cyrk_b200] %s: block %d, %d CTAs/SM, grid %d\n", pe->name(a.method, solve_variant), block, ctas, grid);
+        return 0;
+    };
+    if (pick_grid(two_pass ? VAR_STEPS : variant)) return -1;
 
     // ---- host buffers + final-state variant + a batch worth cutting up: pipelined copy/compute path
     if (!device_io && variant == VAR_LEAN && B >= (size_t(1) << 21))
@@ -625,6 +692,102 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     if (dense) dense_cap = a.expected_size ? a.expected_size + 1 : 257;
     if (a.n_events) ev_cap = a.expected_size ? a.expected_size : 64;
 
+    size_t p_scap = a.expected_size ? a.expected_size + 1 : 257, p_mx = 0;
+    BatchParams p_steps;
+    if (two_pass) {
+        // ---- pass A: final-state solve that records (t, y, step) of every booked step
+        size_t& scap = p_scap;
+        const bool rows_are_steps = want_rows && a.n_t_eval == 0;     // the step records ARE the requested rows
+        BatchParams& pa = p_steps;
+        pa = p;
+        pa.t_eval = nullptr; pa.n_t_eval = 0; pa.dense_output = 0;
+        DevBuf& bt = rows_are_steps ? h->d_trows : h->d_st_t;
+        DevBuf& by = rows_are_steps ? h->d_yrows : h->d_st_y;
+        for (int pass = 0; pass < 2; pass++) {
+            if (bt.ensure(B * scap * 8) || by.ensure(B * scap * NY * 8) || h->d_st_h.ensure(B * scap * 8)) return -1;
+            pa.t_rows = bt.as<double>(); pa.y_rows = by.as<double>(); pa.h_rows = h->d_st_h.as<double>();
+            pa.row_cap = (unsigned)scap;
+            CU_TRY(cudaMemsetAsync(h->d_queue.p, 0, 8, h->stream));
+            CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
+            if (use_prep) {
+                if (h->d_prep.ensure(B * (NDY + 2) * 8)) return -1;
+                const int pgrid = (int)std::min<unsigned long long>((B + 255) / 256, (unsigned long long)device_sm_count(h->device) * 16);
+                if (pe->prep(a.method, pa, h->d_prep.as<double>(), pgrid, 256, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("prep kernel launch failed"); return -1; }
+                h->launches++;
+                pa.prep = h->d_prep.as<double>();
+            }
+            if (pe->launch(a.method, VAR_STEPS, pa, grid, block, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("solve kernel launch failed"); return -1; }
+            h->launches++;
+            CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
+            if (download(h, h->h_size, h->d_size, B * 4)) return -1;
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; }
+            size_t mx = 0;
+            { const unsigned* sz = h->h_size.as<unsigned>(); for (size_t i = 0; i < B; i++) mx = std::max<size_t>(mx, sz[i]); }
+            p_mx = mx;
+            if (mx <= scap) break;
+            if (pass == 1) { set_error("internal: arena overflow after the exact-capacity re-run"); return -1; }
+            if (!dense && !rows_are_steps) {
+                // t_eval only: the per-trajectory kernel needs no per-step storage at all.  When some trajectory takes so
+                // many steps that the records would eat the device (stiff / diverging problems), go back to it.
+                size_t fr = 0, tot = 0;
+                cudaMemGetInfo(&fr, &tot);
+                const size_t have = bt.cap + by.cap + h->d_st_h.cap;
+                if ((double)B * (double)mx * (16.0 + 8.0 * NY) > 0.5 * (double)(fr + have)) { two_pass = false; break; }
+            }
+            scap = mx;      // deterministic re-run with the exact capacity
+        }
+        if (!two_pass) { h->d_st_t.release(); h->d_st_y.release(); h->d_st_h.release(); h->kernel_ms = 0.f; if (pick_grid(variant)) return -1; }
+    }
+    if (two_pass) {
+        const size_t scap = p_scap;
+        const bool rows_are_steps = want_rows && a.n_t_eval == 0;
+        // ---- pass B: one thread per (trajectory, booked step): interpolant, dense record, t_eval samples
+        row_cap = rows_are_steps ? scap : (want_rows ? a.n_t_eval : 0);
+        dense_cap = dense ? scap : 0;
+        StepDenseParams q;
+        memset(&q, 0, sizeof(q));
+        q.n_traj = B; q.step_cap = (unsigned)scap; q.step_threads = (unsigned)std::max<size_t>(1, std::min(p_mx, scap));
+        q.steps_taken = p.steps_taken;
+        q.t_steps = p_steps.t_rows; q.h_steps = p_steps.h_rows; q.y_steps = p_steps.y_rows;
+        q.args = p.args; q.args_stride = p.args_stride;
+        q.t_span = p.t_span; q.t_span_stride = p.t_span_stride;
+        q.t_eval = p.t_eval; q.n_t_eval = p.n_t_eval;
+        if (a.n_t_eval) {
+            if (h->d_trows.ensure(B * row_cap * 8) || h->d_yrows.ensure(B * row_cap * NDY * 8)) return -1;
+            q.t_rows = h->d_trows.as<double>(); q.y_rows = h->d_yrows.as<double>(); q.row_cap = (unsigned)row_cap;
+        }
+        q.dense_output = dense ? 1 : 0;
+        if (dense) {
+            if (h->d_dense_t.ensure(B * dense_cap * 8) ||
+                h->d_dense_state.ensure(B * dense_cap * NY * (q_order + 1) * 8) || h->d_dense_count.ensure(B * 4))
+                return -1;
+            q.dense_t = h->d_dense_t.as<double>(); q.dense_state = h->d_dense_state.as<double>();
+            q.dense_count = h->d_dense_count.as<unsigned>(); q.dense_cap = (unsigned)dense_cap;
+        }
+        q.nfev = p.nfev;
+        CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
+        {
+            const unsigned long long threads = (unsigned long long)B * q.step_threads;
+            const int sblock = 128;
+            const unsigned long long sgrid = (threads + sblock - 1) / sblock;
+            if (sgrid > 0x7fffffffull) { set_error("batch x step capacity too large for one launch: split the batch"); return -1; }
+            if (pe->step_dense(a.method, q, (int)sgrid, sblock, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("step_dense kernel launch failed"); return -1; }
+            h->launches++;
+        }
+        if (a.n_t_eval) {
+            teval_last_kernel<<<(unsigned)((B + 255) / 256), 256, 0, h->stream>>>(B, p.steps_taken, q.t_steps, q.step_cap, p.t_span, p.t_span_stride,
+                                                                                p.t_eval, p.n_t_eval, q.t_rows, q.y_rows, q.row_cap, (unsigned)NDY,
+                                                                                p.size, p.t_last, p.y_last);
+            CU_TRY(cudaGetLastError());
+            h->launches++;
+        }
+        CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
+        if (a.n_t_eval && download(h, h->h_size, h->d_size, B * 4)) return -1;
+        if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; }
+    } else
     for (int pass = 0; pass < 2; pass++) {
         if (want_rows) {
             if (h->d_trows.ensure(B * row_cap * 8) || h->d_yrows.ensure(B * row_cap * NDY * 8)) return -1;
@@ -1418,6 +1581,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "ctas_per_sm")) { g_opt_ctas_per_sm = value; return 0; }
     if (!strcmp(name, "prep")) { g_opt_prep = value; return 0; }
     if (!strcmp(name, "root_batch")) { g_opt_root_batch = value; return 0; }
+    if (!strcmp(name, "two_pass")) { g_opt_two_pass = value; return 0; }
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
     if (!strcmp(name, "cta_kernel")) { g_opt_cta_kernel = value; return 0; }

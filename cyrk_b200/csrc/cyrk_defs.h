@@ -43,7 +43,9 @@ enum Variant : int {
     VAR_LEAN = 0,   // final row + counters only: no t_eval, no dense store, no events, no row store
     VAR_ROWS = 1,   // + row store (every accepted step, or the t_eval samples) + dense-interpolant store
     VAR_FULL = 2,   // + events
-    VAR_COUNT = 3
+    VAR_STEPS = 3,  // VAR_LEAN + one record (t, y, signed step) per booked step: first half of the step-parallel
+                    // t_eval / dense-output path (step_dense_kernel rebuilds the interpolants from these records)
+    VAR_COUNT = 4
 };
 
 #define CYRK_MAX_NY 32        // thread-per-trajectory kernels: compile-time n_y up to this
@@ -80,6 +82,7 @@ struct BatchParams {
     double*   t_rows;            // [n_traj][row_cap]
     double*   y_rows;            // [n_traj][row_cap][NDY]
     unsigned  row_cap;
+    double*   h_rows;            // [n_traj][row_cap]  VAR_STEPS only: the signed step each booked step was taken with
     // ---- dense store (VAR_FULL, dense_output): interpolant i covers (dense_t[i-1], dense_t[i]]
     int       dense_output;
     double*   dense_t;           // [n_traj][dense_cap]      t_now of interpolant i (entry 0: t_start)
@@ -119,6 +122,33 @@ struct DenseEvalParams {
     unsigned      args_stride;
     double*       out;           // [n_traj][n_query][NDY]
     int*          code;          // [n_traj]  first non-zero CySolverResult::call status, else 0
+};
+
+// Step-parallel interpolants (step_dense_kernel): one thread per (trajectory, booked step) recomputes the stages of
+// that step from the VAR_STEPS records, builds its interpolant, stores it and emits the t_eval samples the step covers.
+struct StepDenseParams {
+    unsigned long long n_traj;
+    unsigned      step_cap;      // records per trajectory (record 0 = the initial row)
+    unsigned      step_threads;  // threads per trajectory: 1 + the largest steps_taken of the batch (<= step_cap)
+    const unsigned* steps_taken; // [n_traj]
+    const double* t_steps;       // [n_traj][step_cap]
+    const double* h_steps;       // [n_traj][step_cap]
+    const double* y_steps;       // [n_traj][step_cap][NY]
+    const char*   args;
+    unsigned      args_stride;
+    const double* t_span;        // shared or per trajectory (direction only)
+    unsigned      t_span_stride;
+    const double* t_eval;        // ascending (reversed copy for backward runs), shared
+    unsigned      n_t_eval;
+    double*       t_rows;        // [n_traj][row_cap]       t_eval samples (row j = the j-th sample the run passes)
+    double*       y_rows;        // [n_traj][row_cap][NY]
+    unsigned      row_cap;
+    int           dense_output;
+    double*       dense_t;       // as in BatchParams
+    double*       dense_state;
+    unsigned*     dense_count;
+    unsigned      dense_cap;
+    unsigned*     nfev;          // += the interpolant's extra right-hand-side evaluations (DOP853), counted the reference's way
 };
 
 }  // namespace cyrk

@@ -39,12 +39,20 @@ cudaError_t prep(const BatchParams& p, double* out, int grid, int block, cudaStr
     return cudaGetLastError();
 }
 template <int METHOD>
+cudaError_t step_dense(const StepDenseParams& p, int grid, int block, cudaStream_t s)
+{
+    step_dense_kernel<CYRK_INST_PROB, METHOD><<<grid, block, 0, s>>>(p);
+    return cudaGetLastError();
+}
+template <int METHOD>
 void fill(ProblemEntry* e)
 {
     e->solve[METHOD - 3][VAR_LEAN] = {launch<METHOD, VAR_LEAN>, occupancy<METHOD, VAR_LEAN>, CYRK_STR(CYRK_INST_PROB) "/lean"};
     e->solve[METHOD - 3][VAR_ROWS] = {launch<METHOD, VAR_ROWS>, occupancy<METHOD, VAR_ROWS>, CYRK_STR(CYRK_INST_PROB) "/rows"};
     e->solve[METHOD - 3][VAR_FULL] = {launch<METHOD, VAR_FULL>, occupancy<METHOD, VAR_FULL>, CYRK_STR(CYRK_INST_PROB) "/full"};
+    e->solve[METHOD - 3][VAR_STEPS] = {launch<METHOD, VAR_STEPS>, occupancy<METHOD, VAR_STEPS>, CYRK_STR(CYRK_INST_PROB) "/steps"};
     e->dense_eval[METHOD - 3] = dense_eval<METHOD>;
+    e->step_dense[METHOD - 3] = step_dense<METHOD>;
     e->prep[METHOD - 3] = prep<METHOD>;
 }
 

@@ -17,6 +17,8 @@ cudaError_t user_rhs_launch_prep(int rhs_id, int method, bool strict, int device
                                  int block, cudaStream_t s);
 cudaError_t user_rhs_launch_dense(int rhs_id, int method, bool strict, int device, const DenseEvalParams& p, int grid, int block,
                                   cudaStream_t s);
+cudaError_t user_rhs_launch_step_dense(int rhs_id, int method, bool strict, int device, const StepDenseParams& p, int grid, int block,
+                                       cudaStream_t s);
 // Large systems (registered with n_y == 0): the source defines
 //     __device__ double <entry>(unsigned i, double t, const double* y, unsigned n, const char* args);   -> dy_i
 // and, when registered with n_events > 0,

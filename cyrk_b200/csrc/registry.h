@@ -21,6 +21,7 @@ struct ProblemEntry {
     KernelEntry solve[3][VAR_COUNT];     // [method - 3][variant]
     cudaError_t (*dense_eval[3])(const DenseEvalParams&, int grid, int block, cudaStream_t);
     cudaError_t (*prep[3])(const BatchParams&, double* prep, int grid, int block, cudaStream_t);
+    cudaError_t (*step_dense[3])(const StepDenseParams&, int grid, int block, cudaStream_t);
 };
 
 // table[fp_mode][rhs_id]

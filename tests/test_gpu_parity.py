@@ -440,3 +440,76 @@ def test_native_sharded_solve_over_device_list():
         assert np.array_equal(r[0].y, whole[lo].y) and np.array_equal(r[hi - lo - 1].t, whole[hi - 1].t)
     with pytest.raises(c.CyrkB200Error):
         c.cysolve_ivp_batch("lotkavolterra", spans, y0, devices=[0, 99], **kw)       # bad ordinal: nothing leaks, error names the shard
+
+
+def _solve_both_ways(**kw):
+    outs = []
+    try:
+        for two_pass in (0, 2):      # 2: also for t_eval without dense_output (1, the default, keeps that on the one-pass kernel)
+            c.lib().cyrk_b200_set_option(b"two_pass", two_pass)
+            outs.append(c.cysolve_ivp_batch(**kw))
+    finally:
+        c.lib().cyrk_b200_set_option(b"two_pass", 1)
+    return outs
+
+
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fma"])
+@pytest.mark.parametrize("backward", [False, True], ids=["fwd", "bwd"])
+@pytest.mark.parametrize("mode", ["teval", "dense", "teval+dense"])
+@pytest.mark.parametrize("method", ["RK23", "RK45", "DOP853"])
+def test_step_parallel_interpolants_equal_the_one_pass_kernel(method, mode, backward, strict):
+    """t_eval / dense_output without events or extras run as a final-state solve that records its steps plus one
+    thread per (trajectory, step) (rk_core.cuh, step_dense_body).  Redoing a step from (t_old, y_old, step) executes the
+    same instructions on the same inputs, so every output must equal the per-trajectory kernel's BIT FOR BIT -- rows,
+    counters, nfev, stored interpolants (through sol(t)).  t_eval reaches from before t_start (extrapolated by the first
+    step, like the reference's cursor) to exactly t_end; expected_size is too small, so the exact-capacity re-run
+    is exercised too."""
+    rng = np.random.default_rng(11)
+    B = 777
+    # (Lorenz run backward in time blows up: millions of steps -- that case is the host's fallback, not this test)
+    rhs, args = ("lorenz", [10.0, 28.0, 8 / 3]) if method == "DOP853" and not backward else ("lotkavolterra", [1.5, 1, 3, 1])
+    y0 = rng.uniform(1.0, 8.0, (B, 3 if rhs == "lorenz" else 2))
+    t0, t1 = (6.0, 0.0) if backward else (0.0, 6.0)
+    te = np.linspace(t0 + (0.25 if backward else -0.25), t1, 143) if "teval" in mode else None
+    kw = dict(diffeq=rhs, t_span=(t0, t1), y0=y0, method=method, args=args, rtol=1e-6, atol=1e-9, t_eval=te,
+              dense_output="dense" in mode, expected_size=24, strict_fp=strict)
+    a, b = _solve_both_ways(**kw)
+    assert (a.status == 1).all()
+    for name in ("status", "size", "steps_taken", "n_rejected", "nfev", "t_last", "y_last"):
+        assert np.array_equal(getattr(a, name), getattr(b, name), equal_nan=True), name
+    for i in range(B):
+        n = int(a.size[i])
+        assert np.array_equal(a.t_rows[i, :n], b.t_rows[i, :n]) and np.array_equal(a.y_rows[i, :n], b.y_rows[i, :n]), i
+    if "dense" in mode:
+        assert np.array_equal(a.num_interpolates, b.num_interpolates)
+        tq = np.sort(rng.uniform(min(t0, t1), max(t0, t1), 64))
+        (qa, ca), (qb, cb) = a.call(tq), b.call(tq)
+        assert np.array_equal(ca, cb) and np.array_equal(qa, qb)
+
+
+def test_step_parallel_path_failure_statuses_and_fallbacks(oracle):
+    """max_num_steps (-52): same rows, counters and status from both formulations; a t_eval that ends before t_end, a
+    per-trajectory t_span and extra outputs stay on the per-trajectory kernel (results equal by construction) and still
+    match the oracle."""
+    rng = np.random.default_rng(12)
+    y0 = np.stack([rng.uniform(5, 15, 64), rng.uniform(2.5, 7.5, 64)], 1)
+    te = np.linspace(0, 10, 41)
+    kw = dict(diffeq="lotkavolterra", t_span=(0.0, 10.0), y0=y0, method="RK45", args=[1.5, 1, 3, 1], rtol=1e-7, atol=1e-9,
+              t_eval=te, dense_output=True, max_num_steps=50)
+    a, b = _solve_both_ways(**kw)
+    assert (a.status == -52).all() and np.array_equal(a.status, b.status)
+    for name in ("size", "steps_taken", "nfev", "t_last", "y_last", "num_interpolates"):
+        assert np.array_equal(getattr(a, name), getattr(b, name), equal_nan=True), name
+    for i in range(64):
+        n = int(a.size[i])
+        assert np.array_equal(a.y_rows[i, :n], b.y_rows[i, :n])
+    ob = oracle.solve_batch("lotkavolterra", (0.0, 10.0), y0, "RK45", 1e-7, 1e-9, args=[1.5, 1, 3, 1], t_eval=te,
+                            dense_output=True, max_num_steps=50, impl="port")
+    assert np.array_equal(b.status, ob["status"]) and np.array_equal(b.size, ob["size"]) and np.array_equal(b.nfev, ob["nfev"])
+    # t_eval exhausted at t = 5 < t_end: the reference then saves raw steps again (quirk 6) -> per-trajectory kernel
+    kw.update(t_eval=np.linspace(0, 5, 11), max_num_steps=0)
+    a, b = _solve_both_ways(**kw)
+    assert (a.status == 1).all() and np.array_equal(a.size, b.size) and a.launches == b.launches
+    ref = oracle.solve("lotkavolterra", (0.0, 10.0), y0[0], "RK45", 1e-7, 1e-9, args=[1.5, 1, 3, 1], t_eval=np.linspace(0, 5, 11),
+                       dense_output=True)
+    assert b[0].size == ref.size and np.allclose(b[0].t, ref.t, rtol=1e-6, atol=1e-12)
