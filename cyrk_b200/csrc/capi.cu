@@ -704,6 +704,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         DevBuf& bt = rows_are_steps ? h->d_trows : h->d_st_t;
         DevBuf& by = rows_are_steps ? h->d_yrows : h->d_st_y;
         for (int pass = 0; pass < 2; pass++) {
+            scap = (scap + 31) / 32 * 32;       // whole warps per trajectory in step_dense_kernel
             if (bt.ensure(B * scap * 8) || by.ensure(B * scap * NY * 8) || h->d_st_h.ensure(B * scap * 8)) return -1;
             pa.t_rows = bt.as<double>(); pa.y_rows = by.as<double>(); pa.h_rows = h->d_st_h.as<double>();
             pa.row_cap = (unsigned)scap;
@@ -747,7 +748,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         dense_cap = dense ? scap : 0;
         StepDenseParams q;
         memset(&q, 0, sizeof(q));
-        q.n_traj = B; q.step_cap = (unsigned)scap; q.step_threads = (unsigned)std::max<size_t>(1, std::min(p_mx, scap));
+        q.n_traj = B; q.step_cap = (unsigned)scap; q.step_threads = (unsigned)std::min((std::max<size_t>(1, p_mx) + 31) / 32 * 32, scap);
         q.steps_taken = p.steps_taken;
         q.t_steps = p_steps.t_rows; q.h_steps = p_steps.h_rows; q.y_steps = p_steps.y_rows;
         q.args = p.args; q.args_stride = p.args_stride;
@@ -769,7 +770,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
         {
             const unsigned long long threads = (unsigned long long)B * q.step_threads;
-            const int sblock = 128;
+            const int sblock = CYRK_STEP_DENSE_BLOCK;
             const unsigned long long sgrid = (threads + sblock - 1) / sblock;
             if (sgrid > 0x7fffffffull) { set_error("batch x step capacity too large for one launch: split the batch"); return -1; }
             if (pe->step_dense(a.method, q, (int)sgrid, sblock, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("step_dense kernel launch failed"); return -1; }

@@ -50,6 +50,7 @@ enum Variant : int {
 
 #define CYRK_MAX_NY 32        // thread-per-trajectory kernels: compile-time n_y up to this
 #define CYRK_MAX_EVENTS 8
+#define CYRK_STEP_DENSE_BLOCK 128   // threads per CTA of step_dense_kernel (its shared-memory staging is sized for it)
 
 // One launch of the thread-per-trajectory solver.  Passed by value (constant bank).
 struct BatchParams {
