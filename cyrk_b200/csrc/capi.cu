@@ -167,7 +167,7 @@ struct Handle {
     DevBuf d_trows, d_yrows, d_dense_t, d_dense_state, d_dense_count;
     DevBuf d_ev_t, d_ev_y, d_ev_count, d_ev_term;
     DevBuf d_q_t, d_q_out, d_q_code, d_scratch, d_prep, d_rtol, d_atol;
-    DevBuf d_st_t, d_st_h, d_st_y;          // step records of the two-pass t_eval / dense path
+    DevBuf d_st;                            // step records of the two-pass t_eval / dense path
     // pinned host mirrors
     PinBuf h_status, h_size, h_steps, h_nrej, h_nfev, h_tlast, h_ylast;
     PinBuf h_trows, h_yrows, h_dense_count, h_ev_t, h_ev_y, h_ev_count, h_ev_term;
@@ -204,7 +204,7 @@ struct Handle {
         DevBuf* dbs[] = {&d_y0, &d_args, &d_tspan, &d_teval, &d_queue, &d_status, &d_size, &d_steps, &d_nrej, &d_nfev,
                          &d_tlast, &d_ylast, &d_trows, &d_yrows, &d_dense_t, &d_dense_state, &d_dense_count, &d_ev_t,
                          &d_ev_y, &d_ev_count, &d_ev_term, &d_q_t, &d_q_out, &d_q_code, &d_scratch, &d_prep, &d_rtol, &d_atol,
-                         &d_st_t, &d_st_h, &d_st_y};
+                         &d_st};
         for (DevBuf* b : dbs) b->release();
         PinBuf* pbs[] = {&h_status, &h_size, &h_steps, &h_nrej, &h_nfev, &h_tlast, &h_ylast, &h_trows, &h_yrows,
                          &h_dense_count, &h_ev_t, &h_ev_y, &h_ev_count, &h_ev_term, &h_stage};
@@ -474,7 +474,7 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
 // cysolver.cpp:848-878) and the last saved row, per trajectory.
 __global__ void teval_last_kernel(unsigned long long n_traj, const unsigned* __restrict__ steps, const double* __restrict__ t_steps,
                                   unsigned step_cap, const double* __restrict__ t_span, unsigned t_span_stride,
-                                  const double* __restrict__ t_eval, unsigned n_t_eval, const double* __restrict__ t_rows,
+                                  unsigned rec_doubles, const double* __restrict__ t_eval, unsigned n_t_eval, const double* __restrict__ t_rows,
                                   const double* __restrict__ y_rows, unsigned row_cap, unsigned ndy, unsigned* __restrict__ size,
                                   double* __restrict__ t_last, double* __restrict__ y_last)
 {
@@ -485,7 +485,7 @@ __global__ void teval_last_kernel(unsigned long long n_traj, const unsigned* __r
     const bool fwd = (ts[1] - ts[0]) >= 0.0;
     unsigned sz = 0;
     if (ns > 0) {
-        const double x = t_steps[traj * step_cap + ns];
+        const double x = t_steps[(traj * step_cap + ns) * rec_doubles];
         unsigned a = 0, b = n_t_eval;
         while (a < b) {
             const unsigned m = (a + b) >> 1;
@@ -701,12 +701,11 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         BatchParams& pa = p_steps;
         pa = p;
         pa.t_eval = nullptr; pa.n_t_eval = 0; pa.dense_output = 0;
-        DevBuf& bt = rows_are_steps ? h->d_trows : h->d_st_t;
-        DevBuf& by = rows_are_steps ? h->d_yrows : h->d_st_y;
+        const size_t RA = CYRK_STEP_REC_DOUBLES(NY);
         for (int pass = 0; pass < 2; pass++) {
             scap = (scap + 31) / 32 * 32;       // whole warps per trajectory in step_dense_kernel
-            if (bt.ensure(B * scap * 8) || by.ensure(B * scap * NY * 8) || h->d_st_h.ensure(B * scap * 8)) return -1;
-            pa.t_rows = bt.as<double>(); pa.y_rows = by.as<double>(); pa.h_rows = h->d_st_h.as<double>();
+            if (h->d_st.ensure(B * scap * RA * 8)) return -1;
+            pa.t_rows = nullptr; pa.y_rows = nullptr; pa.step_recs = h->d_st.as<double>();
             pa.row_cap = (unsigned)scap;
             CU_TRY(cudaMemsetAsync(h->d_queue.p, 0, 8, h->stream));
             CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
@@ -722,7 +721,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
             if (download(h, h->h_size, h->d_size, B * 4)) return -1;
             CU_TRY(cudaStreamSynchronize(h->stream));
-            { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; }
+            { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; if (getenv("CYRK_B200_DEBUG")) fprintf(stderr, "[cyrk_b200] step-recording solve: %.3f ms\n", ms); }
             size_t mx = 0;
             { const unsigned* sz = h->h_size.as<unsigned>(); for (size_t i = 0; i < B; i++) mx = std::max<size_t>(mx, sz[i]); }
             p_mx = mx;
@@ -733,12 +732,11 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
                 // many steps that the records would eat the device (stiff / diverging problems), go back to it.
                 size_t fr = 0, tot = 0;
                 cudaMemGetInfo(&fr, &tot);
-                const size_t have = bt.cap + by.cap + h->d_st_h.cap;
-                if ((double)B * (double)mx * (16.0 + 8.0 * NY) > 0.5 * (double)(fr + have)) { two_pass = false; break; }
+                if ((double)B * (double)mx * (8.0 * RA) > 0.5 * (double)(fr + h->d_st.cap)) { two_pass = false; break; }
             }
             scap = mx;      // deterministic re-run with the exact capacity
         }
-        if (!two_pass) { h->d_st_t.release(); h->d_st_y.release(); h->d_st_h.release(); h->kernel_ms = 0.f; if (pick_grid(variant)) return -1; }
+        if (!two_pass) { h->d_st.release(); h->kernel_ms = 0.f; if (pick_grid(variant)) return -1; }
     }
     if (two_pass) {
         const size_t scap = p_scap;
@@ -750,11 +748,11 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         memset(&q, 0, sizeof(q));
         q.n_traj = B; q.step_cap = (unsigned)scap; q.step_threads = (unsigned)std::min((std::max<size_t>(1, p_mx) + 31) / 32 * 32, scap);
         q.steps_taken = p.steps_taken;
-        q.t_steps = p_steps.t_rows; q.h_steps = p_steps.h_rows; q.y_steps = p_steps.y_rows;
+        q.recs = p_steps.step_recs; q.rows_are_steps = rows_are_steps ? 1 : 0;
         q.args = p.args; q.args_stride = p.args_stride;
         q.t_span = p.t_span; q.t_span_stride = p.t_span_stride;
         q.t_eval = p.t_eval; q.n_t_eval = p.n_t_eval;
-        if (a.n_t_eval) {
+        if (a.n_t_eval || rows_are_steps) {
             if (h->d_trows.ensure(B * row_cap * 8) || h->d_yrows.ensure(B * row_cap * NDY * 8)) return -1;
             q.t_rows = h->d_trows.as<double>(); q.y_rows = h->d_yrows.as<double>(); q.row_cap = (unsigned)row_cap;
         }
@@ -777,8 +775,8 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             h->launches++;
         }
         if (a.n_t_eval) {
-            teval_last_kernel<<<(unsigned)((B + 255) / 256), 256, 0, h->stream>>>(B, p.steps_taken, q.t_steps, q.step_cap, p.t_span, p.t_span_stride,
-                                                                                p.t_eval, p.n_t_eval, q.t_rows, q.y_rows, q.row_cap, (unsigned)NDY,
+            teval_last_kernel<<<(unsigned)((B + 255) / 256), 256, 0, h->stream>>>(B, p.steps_taken, q.recs, q.step_cap, p.t_span, p.t_span_stride,
+                                                                                (unsigned)CYRK_STEP_REC_DOUBLES(NY), p.t_eval, p.n_t_eval, q.t_rows, q.y_rows, q.row_cap, (unsigned)NDY,
                                                                                 p.size, p.t_last, p.y_last);
             CU_TRY(cudaGetLastError());
             h->launches++;
@@ -787,7 +785,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         if (a.n_t_eval && download(h, h->h_size, h->d_size, B * 4)) return -1;
         if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
         CU_TRY(cudaStreamSynchronize(h->stream));
-        { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; }
+        { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; if (getenv("CYRK_B200_DEBUG")) fprintf(stderr, "[cyrk_b200] step_dense (+ last row): %.3f ms, %u threads per trajectory\n", ms, q.step_threads); }
     } else
     for (int pass = 0; pass < 2; pass++) {
         if (want_rows) {

@@ -50,6 +50,8 @@ enum Variant : int {
 
 #define CYRK_MAX_NY 32        // thread-per-trajectory kernels: compile-time n_y up to this
 #define CYRK_MAX_EVENTS 8
+// one record of the VAR_STEPS solve: t, signed step, y[NY], padded to whole 16-byte pairs (128-bit stores / loads)
+#define CYRK_STEP_REC_DOUBLES(ny) (((ny) + 3) & ~1)
 #define CYRK_STEP_DENSE_BLOCK 128   // threads per CTA of step_dense_kernel (its shared-memory staging is sized for it)
 
 // One launch of the thread-per-trajectory solver.  Passed by value (constant bank).
@@ -83,7 +85,7 @@ struct BatchParams {
     double*   t_rows;            // [n_traj][row_cap]
     double*   y_rows;            // [n_traj][row_cap][NDY]
     unsigned  row_cap;
-    double*   h_rows;            // [n_traj][row_cap]  VAR_STEPS only: the signed step each booked step was taken with
+    double*   step_recs;         // VAR_STEPS only: [n_traj][row_cap][CYRK_STEP_REC_DOUBLES(NY)] = (t, signed step, y[NY], pad)
     // ---- dense store (VAR_FULL, dense_output): interpolant i covers (dense_t[i-1], dense_t[i]]
     int       dense_output;
     double*   dense_t;           // [n_traj][dense_cap]      t_now of interpolant i (entry 0: t_start)
@@ -132,9 +134,8 @@ struct StepDenseParams {
     unsigned      step_cap;      // records per trajectory (record 0 = the initial row)
     unsigned      step_threads;  // threads per trajectory: 1 + the largest steps_taken of the batch (<= step_cap)
     const unsigned* steps_taken; // [n_traj]
-    const double* t_steps;       // [n_traj][step_cap]
-    const double* h_steps;       // [n_traj][step_cap]
-    const double* y_steps;       // [n_traj][step_cap][NY]
+    const double* recs;          // [n_traj][step_cap][CYRK_STEP_REC_DOUBLES(NY)]  (t, signed step, y[NY], pad)
+    int           rows_are_steps;// no t_eval and the caller wants rows: t_rows / y_rows receive the step records (row s = step s)
     const char*   args;
     unsigned      args_stride;
     const double* t_span;        // shared or per trajectory (direction only)
