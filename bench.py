@@ -46,6 +46,10 @@ NCU_TRAFFIC_BYTES = {"C5": 831.9e6}
 C_M = {"RK23": 25, "RK45": 62, "DOP853": 167}
 E_M = {"RK23": 3, "RK45": 6, "DOP853": 12}
 S_CTRL = {"RK23": 16, "RK45": 22, "DOP853": 34}
+# per interpolant built / per interpolated point, per component; DOP853 builds cost 3 more RHS evaluations
+F_DENSE = {"RK23": 11, "RK45": 33, "DOP853": 155}
+F_INTERP = {"RK23": 10, "RK45": 13, "DOP853": 15}
+Q_ORDER = {"RK23": 3, "RK45": 4, "DOP853": 7}
 
 WORKLOADS = {
     # name: rhs, method, n_y, F_rhs, rtol, atol, per-GPU batch, description
@@ -299,6 +303,7 @@ def main():
     ok = bool(((res.status == 1) | (res.status == 2)).all())
     attempts = int(res.steps_taken.sum(dtype=np.int64)) + int(res.n_rejected.sum(dtype=np.int64))
     steps_acc = int(res.steps_taken.sum(dtype=np.int64))
+    rows_saved = int(res.size.sum(dtype=np.int64))
     res.close()
 
     # ---- max over ranks
@@ -320,11 +325,20 @@ def main():
         f_attempt = w["ny"] * C_M[w["method"]] + E_M[w["method"]] * w["f_rhs"] + S_CTRL[w["method"]]
         # per-GPU kernel roofline (rank 0's counters; every rank runs the same-size shard)
         alg_flops_per_launch = attempts * f_attempt
+        kw_w = w.get("kwargs", {})
+        if kw_w.get("dense_output"):       # one interpolant per accepted step
+            alg_flops_per_launch += steps_acc * (w["ny"] * F_DENSE[w["method"]] + (3 * w["f_rhs"] if w["method"] == "DOP853" else 0))
+        if "t_eval" in kw_w:               # one interpolated point per saved row
+            alg_flops_per_launch += rows_saved * w["ny"] * F_INTERP[w["method"]]
         ker_ms_per_launch = ker_ms / a.steps
         achieved_tf = alg_flops_per_launch / (ker_ms_per_launch * 1e-3) / 1e12
         io_bytes = B * (w["ny"] * 8 + 5 * 4 + 8 + w["ny"] * 8)      # y0 in; counters, t_last, y_last out
         if w.get("kwargs", {}).get("store") == "rows" and "t_eval" not in w.get("kwargs", {}):
             io_bytes += (steps_acc + B) * (w["ny"] + 1) * 8           # every accepted row (t, y) of this rank
+        if kw_w.get("store") == "rows" and "t_eval" in kw_w:
+            io_bytes += rows_saved * (w["ny"] + 1) * 8                # every t_eval sample (t, y)
+        if kw_w.get("dense_output"):                                  # stored interpolants: t_now + [y_old | Q] per step
+            io_bytes += (steps_acc + B) * (1 + w["ny"] * (Q_ORDER[w["method"]] + 1)) * 8
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]

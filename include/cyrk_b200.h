@@ -238,7 +238,9 @@ size_t   cyrk_b200_get_d2h_bytes(void* h);
  * 0 = by occupancy), "ctas_per_sm" (0 = occupancy API), "prep" (start-up kernel: -1 auto / 0 / 1), "root_batch" (1..32),
  * "cta_kernel" (0 = register-resident CTA kernel where it applies, 1 = shared-memory/slab kernel), "cta_block",
  * "cta_smem_vecs" (slab kernel only), "pipe_chunk" (trajectories per chunk of the pipelined host-I/O path),
- * "pipe_taper" (short first/last chunks, 0/1). */
+ * "pipe_taper" (short first/last chunks, 0/1), "two_pass" (dense_output / t_eval without events or extras: 1 = step-parallel
+ * interpolants when dense_output is set [default], 2 = also for t_eval alone, 0 = always the per-trajectory kernel; the
+ * results are bitwise identical either way). */
 int      cyrk_b200_set_option(const char* name, int value);
 /* FP64 FMA throughput probe (dependent-free DFMA streams on every SM): returns TFLOP/s. */
 double   cyrk_b200_measure_fp64_tflops(int device);
