@@ -94,6 +94,7 @@ static int g_opt_pipe_chunk = 1 << 20; // pipelined host-I/O path: trajectories 
 static int g_opt_cta_kernel = 0;      // CTA path: 0 = pick (register-resident kernel where it is faster), 1 = always the
                                       // shared-memory/slab kernel, 2 = the register-resident kernel whenever n_y <= 4096
 static int g_opt_two_pass = 1;        // t_eval / dense_output without events or extras: step-parallel interpolants (0 = the one-pass kernel)
+static int g_opt_events_variant = 1;  // events with store='final' and no t_eval / dense store: the VAR_EVENTS kernels (0 = VAR_FULL)
 static int g_opt_root_batch = 12;     // measured: 8..16 is the flat optimum on the C3 workload (profiles/r01_notes.md)
 static int g_opt_ctas_per_sm = 0;
 
@@ -512,7 +513,8 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     const bool device_io = (a.flags & CYRK_FLAG_DEVICE_IO) != 0;
     const bool want_rows = a.store_mode == CYRK_STORE_ROWS;
     const bool dense = a.dense_output != 0;
-    const int variant = a.n_events > 0 ? VAR_FULL : ((dense || want_rows || a.n_t_eval > 0) ? VAR_ROWS : VAR_LEAN);
+    const bool stores = dense || want_rows || a.n_t_eval > 0;
+    const int variant = a.n_events > 0 ? ((stores || !g_opt_events_variant) ? VAR_FULL : VAR_EVENTS) : (stores ? VAR_ROWS : VAR_LEAN);
     const int q_order = a.method == CYRK_METHOD_RK23 ? 3 : a.method == CYRK_METHOD_RK45 ? 4 : 7;
 
     // Step-parallel interpolants (rk_core.cuh, step_dense_body): a final-state solve that records its booked steps, then one
@@ -1581,6 +1583,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "prep")) { g_opt_prep = value; return 0; }
     if (!strcmp(name, "root_batch")) { g_opt_root_batch = value; return 0; }
     if (!strcmp(name, "two_pass")) { g_opt_two_pass = value; return 0; }
+    if (!strcmp(name, "events_variant")) { g_opt_events_variant = value; return 0; }
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
     if (!strcmp(name, "cta_kernel")) { g_opt_cta_kernel = value; return 0; }

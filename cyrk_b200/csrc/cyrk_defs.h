@@ -45,7 +45,9 @@ enum Variant : int {
     VAR_FULL = 2,   // + events
     VAR_STEPS = 3,  // VAR_LEAN + one record (t, y, signed step) per booked step: first half of the step-parallel
                     // t_eval / dense-output path (step_dense_kernel rebuilds the interpolants from these records)
-    VAR_COUNT = 4
+    VAR_EVENTS = 4, // VAR_FULL without the row store, the t_eval emission and the dense store (store='final' + events):
+                    // the same decisions from ~25 % less code -- the events kernels are instruction-fetch bound
+    VAR_COUNT = 5
 };
 
 #define CYRK_MAX_NY 32        // thread-per-trajectory kernels: compile-time n_y up to this

@@ -15,16 +15,27 @@ namespace cyrk {
 namespace CYRK_FP_NS {
 namespace {
 
+// events + storage, RK23 / RK45: the register-capped definition (rk_core.cuh); DOP853 would spill 500 bytes under the cap
+#ifndef CYRK_FULL_CAP
+#define CYRK_FULL_CAP 1
+#endif
+template <int METHOD, int VAR>
+constexpr bool capped() { return CYRK_FULL_CAP && VAR == VAR_FULL && METHOD != METHOD_DOP853; }
+
 template <int METHOD, int VAR>
 cudaError_t launch(const BatchParams& p, int grid, int block, cudaStream_t s)
 {
-    rk_thread_kernel<CYRK_INST_PROB, METHOD, VAR><<<grid, block, 0, s>>>(p);
+    if constexpr (capped<METHOD, VAR>()) rk_thread_kernel_capped<CYRK_INST_PROB, METHOD, VAR><<<grid, block, 0, s>>>(p);
+    else rk_thread_kernel<CYRK_INST_PROB, METHOD, VAR><<<grid, block, 0, s>>>(p);
     return cudaGetLastError();
 }
 template <int METHOD, int VAR>
 cudaError_t occupancy(int* ctas, int block)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, rk_thread_kernel<CYRK_INST_PROB, METHOD, VAR>, block, 0);
+    if constexpr (capped<METHOD, VAR>())
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, rk_thread_kernel_capped<CYRK_INST_PROB, METHOD, VAR>, block, 0);
+    else
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, rk_thread_kernel<CYRK_INST_PROB, METHOD, VAR>, block, 0);
 }
 template <int METHOD>
 cudaError_t dense_eval(const DenseEvalParams& p, int grid, int block, cudaStream_t s)
@@ -51,6 +62,7 @@ void fill(ProblemEntry* e)
     e->solve[METHOD - 3][VAR_ROWS] = {launch<METHOD, VAR_ROWS>, occupancy<METHOD, VAR_ROWS>, CYRK_STR(CYRK_INST_PROB) "/rows"};
     e->solve[METHOD - 3][VAR_FULL] = {launch<METHOD, VAR_FULL>, occupancy<METHOD, VAR_FULL>, CYRK_STR(CYRK_INST_PROB) "/full"};
     e->solve[METHOD - 3][VAR_STEPS] = {launch<METHOD, VAR_STEPS>, occupancy<METHOD, VAR_STEPS>, CYRK_STR(CYRK_INST_PROB) "/steps"};
+    e->solve[METHOD - 3][VAR_EVENTS] = {launch<METHOD, VAR_EVENTS>, occupancy<METHOD, VAR_EVENTS>, CYRK_STR(CYRK_INST_PROB) "/events"};
     e->dense_eval[METHOD - 3] = dense_eval<METHOD>;
     e->step_dense[METHOD - 3] = step_dense<METHOD>;
     e->prep[METHOD - 3] = prep<METHOD>;
