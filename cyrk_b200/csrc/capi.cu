@@ -169,6 +169,7 @@ struct Handle {
     DevBuf d_ev_t, d_ev_y, d_ev_count, d_ev_term;
     DevBuf d_q_t, d_q_out, d_q_code, d_scratch, d_prep, d_rtol, d_atol;
     DevBuf d_st;                            // step records of the two-pass t_eval / dense path
+    DevBuf d_ev_t2, d_ev_y2;                // re-packed event arenas
     // pinned host mirrors
     PinBuf h_status, h_size, h_steps, h_nrej, h_nfev, h_tlast, h_ylast;
     PinBuf h_trows, h_yrows, h_dense_count, h_ev_t, h_ev_y, h_ev_count, h_ev_term;
@@ -205,7 +206,7 @@ struct Handle {
         DevBuf* dbs[] = {&d_y0, &d_args, &d_tspan, &d_teval, &d_queue, &d_status, &d_size, &d_steps, &d_nrej, &d_nfev,
                          &d_tlast, &d_ylast, &d_trows, &d_yrows, &d_dense_t, &d_dense_state, &d_dense_count, &d_ev_t,
                          &d_ev_y, &d_ev_count, &d_ev_term, &d_q_t, &d_q_out, &d_q_code, &d_scratch, &d_prep, &d_rtol, &d_atol,
-                         &d_st};
+                         &d_st, &d_ev_t2, &d_ev_y2};
         for (DevBuf* b : dbs) b->release();
         PinBuf* pbs[] = {&h_status, &h_size, &h_steps, &h_nrej, &h_nfev, &h_tlast, &h_ylast, &h_trows, &h_yrows,
                          &h_dense_count, &h_ev_t, &h_ev_y, &h_ev_count, &h_ev_term, &h_stage};
@@ -507,6 +508,22 @@ __global__ void teval_last_kernel(unsigned long long n_traj, const unsigned* __r
     }
 }
 
+// Event arenas are allocated for `expected_size` hits per event (default 64) but typically hold a handful: before they
+// cross PCIe they are re-packed to the largest count that occurred.
+__global__ void repack_events_kernel(unsigned long long n_lists, unsigned old_cap, unsigned new_cap, unsigned ndy,
+                                     const double* __restrict__ t_in, const double* __restrict__ y_in,
+                                     double* __restrict__ t_out, double* __restrict__ y_out)
+{
+    const unsigned long long total = n_lists * new_cap;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long l = idx / new_cap;
+        const unsigned long long src = l * old_cap + (idx - l * new_cap);
+        t_out[idx] = t_in[src];
+        for (unsigned i = 0; i < ndy; i++) y_out[idx * ndy + i] = y_in[src * ndy + i];
+    }
+}
+
 static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
 {
     const size_t B = a.n_traj, NY = pe->ny, NX = pe->nextra, NDY = NY + NX;
@@ -689,7 +706,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         p.n_t_eval = (unsigned)a.n_t_eval;
     }
 
-    size_t row_cap = 0, dense_cap = 0, ev_cap = 0;
+    size_t row_cap = 0, dense_cap = 0, ev_cap = 0, ev_used = 0;
     if (want_rows) row_cap = a.n_t_eval ? a.n_t_eval : (a.expected_size ? a.expected_size : 256);
     if (dense) dense_cap = a.expected_size ? a.expected_size + 1 : 257;
     if (a.n_events) ev_cap = a.expected_size ? a.expected_size : 64;
@@ -806,6 +823,9 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             p.dense_cap = (unsigned)dense_cap;
         }
         if (a.n_events) {
+            // (a reused handle: the arenas were swapped with their smaller re-packed copies at the end of the last solve)
+            if (h->d_ev_t2.cap > h->d_ev_t.cap) std::swap(h->d_ev_t, h->d_ev_t2);
+            if (h->d_ev_y2.cap > h->d_ev_y.cap) std::swap(h->d_ev_y, h->d_ev_y2);
             if (h->d_ev_t.ensure(B * a.n_events * ev_cap * 8) || h->d_ev_y.ensure(B * a.n_events * ev_cap * NDY * 8) ||
                 h->d_ev_count.ensure(B * a.n_events * 4) || h->d_ev_term.ensure(B * 4))
                 return -1;
@@ -845,12 +865,27 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         if (dense) { const unsigned* s = h->h_dense_count.as<unsigned>(); for (size_t i = 0; i < B; i++) mx_dense = std::max<size_t>(mx_dense, s[i]); }
         if (a.n_events) { const unsigned* s = h->h_ev_count.as<unsigned>(); for (size_t i = 0; i < B * a.n_events; i++) mx_ev = std::max<size_t>(mx_ev, s[i]); }
         const bool overflow = mx_rows > row_cap || mx_dense > dense_cap || mx_ev > ev_cap;
+        ev_used = mx_ev;
         if (!overflow) break;
         if (pass == 1) { set_error("internal: arena overflow after the exact-capacity re-run"); return -1; }
         // deterministic re-run with exact capacities
         row_cap = std::max(row_cap, mx_rows);
         dense_cap = std::max(dense_cap, mx_dense);
         ev_cap = std::max(ev_cap, mx_ev);
+    }
+    if (a.n_events && !device_io && std::max<size_t>(ev_used, 1) * 2 <= ev_cap) {
+        const size_t new_cap = std::max<size_t>(ev_used, 1);
+        if (h->d_ev_t2.ensure(B * a.n_events * new_cap * 8) || h->d_ev_y2.ensure(B * a.n_events * new_cap * NDY * 8)) return -1;
+        const unsigned long long total = (unsigned long long)B * a.n_events * new_cap;
+        const int rgrid = (int)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)device_sm_count(h->device) * 32);
+        repack_events_kernel<<<rgrid, 256, 0, h->stream>>>((unsigned long long)B * a.n_events, (unsigned)ev_cap, (unsigned)new_cap, (unsigned)NDY,
+                                                           h->d_ev_t.as<double>(), h->d_ev_y.as<double>(),
+                                                           h->d_ev_t2.as<double>(), h->d_ev_y2.as<double>());
+        CU_TRY(cudaGetLastError());
+        h->launches++;
+        std::swap(h->d_ev_t, h->d_ev_t2);
+        std::swap(h->d_ev_y, h->d_ev_y2);
+        ev_cap = new_cap;
     }
     h->row_cap = row_cap; h->dense_cap = dense_cap; h->ev_cap = ev_cap;
 
