@@ -54,7 +54,9 @@ enum Variant : int {
 #define CYRK_MAX_EVENTS 8
 // one record of the VAR_STEPS solve: t, signed step, y[NY], padded to whole 16-byte pairs (128-bit stores / loads)
 #define CYRK_STEP_REC_DOUBLES(ny) (((ny) + 3) & ~1)
+#ifndef CYRK_STEP_DENSE_BLOCK
 #define CYRK_STEP_DENSE_BLOCK 128   // threads per CTA of step_dense_kernel (its shared-memory staging is sized for it)
+#endif
 
 // One launch of the thread-per-trajectory solver.  Passed by value (constant bank).
 struct BatchParams {

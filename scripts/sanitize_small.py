@@ -26,4 +26,14 @@ for m in ("RK23", "RK45", "DOP853"):
 src = "__device__ void f(double* dy, double t, const double* y, const char* a) { dy[0] = -y[0] + sin(t); dy[1] = y[0]; dy[2] = y[1] * 2.0; }"
 u = c.UserRHS(src, "f", n_y=2, n_extra=1)
 r = c.cysolve_ivp_batch(u, (0, 2), y0, method="RK45", num_extra=1, rtol=1e-5, atol=1e-8, t_eval=np.linspace(0, 2, 5))
+# step-parallel interpolants: precompiled (Lorenz: 3 components, padded step records) and NVRTC, forward t_eval beyond both ends
+yz = rng.uniform(1.0, 8.0, (B, 3))
+for m in ("RK23", "RK45", "DOP853"):
+    r = c.cysolve_ivp_batch("lorenz", (0, 2), yz, method=m, args=[10.0, 28.0, 8 / 3], rtol=1e-6, atol=1e-9, t_eval=np.linspace(-0.1, 2.1, 97), dense_output=True, expected_size=8)
+    r = c.cysolve_ivp_batch("lorenz", (0, 2), yz, method=m, args=[10.0, 28.0, 8 / 3], rtol=1e-6, atol=1e-9, dense_output=True)
+c.lib().cyrk_b200_set_option(b"two_pass", 2)
+r = c.cysolve_ivp_batch("lorenz", (0, 2), yz, method="DOP853", args=[10.0, 28.0, 8 / 3], rtol=1e-6, atol=1e-9, t_eval=np.linspace(0, 2, 33))
+c.lib().cyrk_b200_set_option(b"two_pass", 1)
+u2 = c.UserRHS("__device__ void g(double* dy, double t, const double* y, const char* a) { dy[0] = -y[0] + sin(t); dy[1] = y[0]; }", "g", n_y=2)
+r = c.cysolve_ivp_batch(u2, (0, 2), y0, method="DOP853", rtol=1e-6, atol=1e-9, t_eval=np.linspace(0, 2, 21), dense_output=True)
 print("sanitize run ok")

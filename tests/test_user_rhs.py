@@ -71,6 +71,33 @@ def test_user_lv_equals_builtin():
 
 
 @pytest.mark.gpu
+def test_user_rhs_dense_and_t_eval_take_the_step_parallel_path():
+    """NVRTC right-hand side + dense_output + t_eval (no events / extras): VAR_STEPS solve + step_dense_body compiled at run
+    time.  Strict build: bitwise equal to the precompiled built-in; both: bitwise equal to the per-trajectory kernel."""
+    u = c.UserRHS(LV_SRC, "my_lv", n_y=2, args_bytes=32)
+    rng = np.random.default_rng(5)
+    B = 300
+    y0 = np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)
+    te = np.linspace(0, 10, 57)
+    tq = np.linspace(0.5, 9.5, 9)
+    for method in ("RK45", "DOP853"):
+        kw = dict(method=method, args=[1.5, 1, 3, 1], rtol=1e-6, atol=1e-8, t_eval=te, dense_output=True)
+        a = c.cysolve_ivp_batch(u, (0, 10), y0, strict_fp=True, **kw)
+        b = c.cysolve_ivp_batch("lotkavolterra", (0, 10), y0, strict_fp=True, **kw)
+        assert a.launches == b.launches >= 3                      # recording solve + step_dense + last row
+        assert np.array_equal(a.size, b.size) and np.array_equal(a.nfev, b.nfev)
+        assert np.array_equal(a.y_rows, b.y_rows) and np.array_equal(a.call(tq)[0], b.call(tq)[0])
+        try:
+            c.lib().cyrk_b200_set_option(b"two_pass", 0)
+            d = c.cysolve_ivp_batch(u, (0, 10), y0, **kw)
+        finally:
+            c.lib().cyrk_b200_set_option(b"two_pass", 1)
+        e = c.cysolve_ivp_batch(u, (0, 10), y0, **kw)
+        assert d.launches < e.launches
+        assert np.array_equal(d.y_rows, e.y_rows) and np.array_equal(d.nfev, e.nfev) and np.array_equal(d.call(tq)[0], e.call(tq)[0])
+
+
+@pytest.mark.gpu
 def test_user_rhs_with_struct_args_events_extras_dense(oracle):
     u = c.UserRHS(DRAG_SRC, "drag", n_y=2, n_extra=1, args_bytes=40, n_events=3)
     rng = np.random.default_rng(1)
