@@ -26,6 +26,10 @@
 // inputs -> identical branches), interpolating its own components of the state for each evaluation.  Not available on
 // this path (the host shim rejects it): extra outputs.
 #pragma once
+
+#ifndef CYRK_EVAL_GROUP
+#define CYRK_EVAL_GROUP 1      // components per right-hand-side call on the register-resident CTA kernel
+#endif
 #include "rk_core.cuh"
 #include "cta_core_params.h"
 
@@ -145,14 +149,41 @@ struct Cta2Solver {
         else return eval_call(i, t, in, n, args, aux);
     }
 
+    // Several components per call (CYRK_EVAL_GROUP, a divisor of C): the callee's constants and the call marshalling
+    // are paid once per group, and the group's dependent chains (range reduction -> polynomial) interleave.  The
+    // struct comes back in registers (checked in SASS: no local memory).
+    template <int W> struct EvalGroup { double v[W]; };
+    template <int W>
+    static __device__ __noinline__ EvalGroup<W> eval_group_call(unsigned i0, unsigned stride, double t, const double* in, unsigned n,
+                                                                const char* args, const double* aux)
+    {
+        EvalGroup<W> r;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const unsigned i = i0 + (unsigned)w * stride;
+            r.v[w] = i < n ? Prob::eval(i, t, in, n, args, aux) : 0.0;
+        }
+        return r;
+    }
+
     // K_J = f(t, in) for the components this thread owns; `in` must be complete (the caller has synchronised)
     template <int J>
     CYRK_DI void eval_rhs(double t, const double* in)
     {
+        constexpr int W = CYRK_EVAL_GROUP;
+        if constexpr (!Prob::INLINE_EVAL && W > 1 && C % W == 0) {
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            const unsigned i = comp(c);
-            kset<J>(c, i < n ? eval_one(i, t, in, n, args, aux) : 0.0);
+            for (int c0 = 0; c0 < C; c0 += W) {
+                const EvalGroup<W> g = eval_group_call<W>(comp(c0), T, t, in, n, args, aux);
+#pragma unroll
+                for (int w = 0; w < W; w++) kset<J>(c0 + w, g.v[w]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const unsigned i = comp(c);
+                kset<J>(c, i < n ? eval_one(i, t, in, n, args, aux) : 0.0);
+            }
         }
         nfev++;
     }

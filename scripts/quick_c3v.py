@@ -9,9 +9,9 @@ y0 = torch.from_numpy(np.stack([rng.uniform(-1.5, 1.5, B), rng.uniform(-1, 1, B)
 args = torch.from_numpy(np.stack([np.ones(B), np.ones(B), np.full(B, 9.81), np.full(B, 1.5), rng.uniform(2.0, 12.0, B)], 1)).cuda()
 ts = torch.tensor([0.0, 10.0], dtype=torch.float64, device="cuda")
 ev = [c.Event("y0"), c.Event("y1", direction=-1), c.Event("t_minus_arg4", terminal=True)]
-for variant in (0, 1):
+for variant in (1,):
     c.lib().cyrk_b200_set_option(b"events_variant", variant)
-    for rb in (8, 12, 16):
+    for rb in (1, 2, 4, 6, 8, 10, 12):
         c.lib().cyrk_b200_set_option(b"root_batch", rb)
         res = None; best = 1e9
         for rep in range(3):
