@@ -93,6 +93,7 @@ static int g_opt_pipe_taper = 1;       // pipelined host-I/O path: short first /
 static int g_opt_pipe_chunk = 1 << 20; // pipelined host-I/O path: trajectories per chunk (at most 32 chunks)
 static int g_opt_cta_kernel = 0;      // CTA path: 0 = pick (register-resident kernel where it is faster), 1 = always the
                                       // shared-memory/slab kernel, 2 = the register-resident kernel whenever n_y <= 4096
+static int g_opt_shared_args = 1;     // shared args through the kernel parameter block (VAR_LEAN_SHARED); 0 = per-lane registers
 static int g_opt_two_pass = 1;        // t_eval / dense_output without events or extras: step-parallel interpolants (0 = the one-pass kernel)
 static int g_opt_events_variant = 1;  // events with store='final' and no t_eval / dense store: the VAR_EVENTS kernels (0 = VAR_FULL)
 static int g_opt_root_batch = 12;     // measured: 8..16 is the flat optimum on the C3 workload (profiles/r01_notes.md)
@@ -353,7 +354,7 @@ static int device_sm_count(int dev)
 //   copy-in stream  ->  two alternating compute streams  ->  copy-out stream
 // so PCIe traffic hides behind the solve kernels, and the tail of one chunk's persistent kernel overlaps the head of the
 // next (they run on different streams).  Results are identical to the single-launch path: trajectories are independent.
-static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* pe, BatchParams p, int grid, int block, bool use_prep)
+static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* pe, BatchParams p, int grid, int block, bool use_prep, int lean_variant)
 {
     const size_t B = a.n_traj, NY = pe->ny, NDY = pe->ny + pe->nextra;
     const size_t args_stride = (size_t)pe->nargs_dbl * sizeof(double);
@@ -446,7 +447,7 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
             q.prep = pr;
             h->launches++;
         }
-        if (pe->launch(a.method, VAR_LEAN, q, cgrid, block, sc) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("solve kernel launch failed"); return -1; }
+        if (pe->launch(a.method, lean_variant, q, cgrid, block, sc) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("solve kernel launch failed"); return -1; }
         h->launches++;
         CU_TRY(cudaEventRecord(e_k1, sc));
         // ---- copy out
@@ -531,7 +532,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     const bool want_rows = a.store_mode == CYRK_STORE_ROWS;
     const bool dense = a.dense_output != 0;
     const bool stores = dense || want_rows || a.n_t_eval > 0;
-    const int variant = a.n_events > 0 ? ((stores || !g_opt_events_variant) ? VAR_FULL : VAR_EVENTS) : (stores ? VAR_ROWS : VAR_LEAN);
+    int variant = a.n_events > 0 ? ((stores || !g_opt_events_variant) ? VAR_FULL : VAR_EVENTS) : (stores ? VAR_ROWS : VAR_LEAN);
     const int q_order = a.method == CYRK_METHOD_RK23 ? 3 : a.method == CYRK_METHOD_RK45 ? 4 : 7;
 
     // Step-parallel interpolants (rk_core.cuh, step_dense_body): a final-state solve that records its booked steps, then one
@@ -562,6 +563,22 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     BatchParams p;
     memset(&p, 0, sizeof(p));
     p.n_traj = B;
+    // Final-state solve of a batch whose args are shared: the values travel in the kernel parameter block and the right-hand
+    // side reads them from the constant bank (VAR_LEAN_SHARED) -- 4 registers per lane fewer for Lotka-Volterra / RK45, which
+    // is the difference between 7 and 8 resident CTAs per SM.
+    if (variant == VAR_LEAN && g_opt_shared_args && pe->nargs_dbl > 0 && pe->nargs_dbl <= CYRK_SHARED_ARGS_MAX && a.n_args <= 1) {
+        const size_t want = (size_t)pe->nargs_dbl * sizeof(double);
+        bool ok = true;
+        if (a.n_args == 1 && a.args != nullptr) {
+            if (device_io) {
+                ok = a.args_len == want && cudaMemcpy(p.shared_args, a.args, want, cudaMemcpyDeviceToHost) == cudaSuccess;
+                if (!ok) cudaGetLastError();
+            } else {
+                memcpy(p.shared_args, a.args, std::min(want, a.args_len));      // (zero padded like the device copy)
+            }
+        }
+        if (ok) variant = VAR_LEAN_SHARED;
+    }
     for (size_t i = 0; i < NY; i++) {
         double r = a.rtols[a.n_rtols > 1 ? i : 0];
         if (r < 100.0 * std::numeric_limits<double>::epsilon()) r = 100.0 * std::numeric_limits<double>::epsilon();
@@ -631,8 +648,8 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     if (pick_grid(two_pass ? VAR_STEPS : variant)) return -1;
 
     // ---- host buffers + final-state variant + a batch worth cutting up: pipelined copy/compute path
-    if (!device_io && variant == VAR_LEAN && B >= (size_t(1) << 21))
-        return solve_lean_pipelined(h, a, pe, p, grid, block, use_prep);
+    if (!device_io && (variant == VAR_LEAN || variant == VAR_LEAN_SHARED) && B >= (size_t(1) << 21))
+        return solve_lean_pipelined(h, a, pe, p, grid, block, use_prep, variant);
 
     // ---- inputs
     const size_t args_stride = (size_t)pe->nargs_dbl * sizeof(double);
@@ -1618,6 +1635,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "prep")) { g_opt_prep = value; return 0; }
     if (!strcmp(name, "root_batch")) { g_opt_root_batch = value; return 0; }
     if (!strcmp(name, "two_pass")) { g_opt_two_pass = value; return 0; }
+    if (!strcmp(name, "shared_args")) { g_opt_shared_args = value; return 0; }
     if (!strcmp(name, "events_variant")) { g_opt_events_variant = value; return 0; }
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }

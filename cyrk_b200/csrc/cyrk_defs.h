@@ -47,8 +47,11 @@ enum Variant : int {
                     // t_eval / dense-output path (step_dense_kernel rebuilds the interpolants from these records)
     VAR_EVENTS = 4, // VAR_FULL without the row store, the t_eval emission and the dense store (store='final' + events):
                     // the same decisions from ~25 % less code -- the events kernels are instruction-fetch bound
-    VAR_COUNT = 5
+    VAR_LEAN_SHARED = 5, // VAR_LEAN for a batch whose args are shared: the right-hand side reads them from the kernel
+                    // parameter block (constant bank / uniform registers) instead of per-lane registers
+    VAR_COUNT = 6
 };
+#define CYRK_SHARED_ARGS_MAX 8     // doubles
 
 #define CYRK_MAX_NY 32        // thread-per-trajectory kernels: compile-time n_y up to this
 #define CYRK_MAX_EVENTS 8
@@ -65,6 +68,7 @@ struct BatchParams {
     const double* y0;            // [n_traj][NY]
     const char*   args;          // shared blob, or [n_traj][args_stride]
     unsigned      args_stride;   // bytes; 0 = shared
+    double        shared_args[CYRK_SHARED_ARGS_MAX];   // VAR_LEAN_SHARED: the shared args themselves
     const double* t_span;        // [2] shared, or [n_traj][2]
     unsigned      t_span_stride; // 0 = shared, 2 = per trajectory
     double rtol[CYRK_MAX_NY];    // already floored at 100*eps on the host (rk.cpp:600-608)

@@ -59,6 +59,7 @@ template <int METHOD>
 void fill(ProblemEntry* e)
 {
     e->solve[METHOD - 3][VAR_LEAN] = {launch<METHOD, VAR_LEAN>, occupancy<METHOD, VAR_LEAN>, CYRK_STR(CYRK_INST_PROB) "/lean"};
+    e->solve[METHOD - 3][VAR_LEAN_SHARED] = {launch<METHOD, VAR_LEAN_SHARED>, occupancy<METHOD, VAR_LEAN_SHARED>, CYRK_STR(CYRK_INST_PROB) "/lean-shared-args"};
     e->solve[METHOD - 3][VAR_ROWS] = {launch<METHOD, VAR_ROWS>, occupancy<METHOD, VAR_ROWS>, CYRK_STR(CYRK_INST_PROB) "/rows"};
     e->solve[METHOD - 3][VAR_FULL] = {launch<METHOD, VAR_FULL>, occupancy<METHOD, VAR_FULL>, CYRK_STR(CYRK_INST_PROB) "/full"};
     e->solve[METHOD - 3][VAR_STEPS] = {launch<METHOD, VAR_STEPS>, occupancy<METHOD, VAR_STEPS>, CYRK_STR(CYRK_INST_PROB) "/steps"};
