@@ -38,9 +38,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # DRAM traffic per launch of the dominant kernel from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum),
-# same workload/batch as the bench line: profiles/r01_ncu_c5_lv_rk45_final2.txt (454.3 MB read + 377.6 MB written;
+# same workload/batch as the bench line: profiles/r01_ncu_c5_lv_rk45_s4_shared_args.txt (486.7 MB read + 406.0 MB written;
 # algorithmic: y0 16 B + start-up record 40 B in, 44 B out per trajectory = 839 MB).
-NCU_TRAFFIC_BYTES = {"C5": 831.9e6}
+NCU_TRAFFIC_BYTES = {"C5": 892.7e6}
 
 # F_attempt(m) = n_y*c_m + E_m*F_rhs + s   
 C_M = {"RK23": 25, "RK45": 62, "DOP853": 167}
@@ -361,7 +361,7 @@ def main():
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak and fp64_peak > 0 else None,
                          "traffic": NCU_TRAFFIC_BYTES.get(a.workload) if B == WORKLOADS[a.workload]["batch"] else None,
-                         "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_c5_lv_rk45_final2.txt)",
+                         "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_c5_lv_rk45_s4_shared_args.txt)",
                          "peak_source": "in-run dependent-free DFMA probe (cyrk_b200_measure_fp64_tflops); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "flop_per_attempt": f_attempt, "kernel_ms_per_launch": ker_ms_per_launch,
