@@ -241,7 +241,8 @@ size_t   cyrk_b200_get_d2h_bytes(void* h);
  * "pipe_taper" (short first/last chunks, 0/1), "two_pass" (dense_output / t_eval without events or extras: 1 = step-parallel
  * interpolants when dense_output is set [default], 2 = also for t_eval alone, 0 = always the per-trajectory kernel; the
  * results are bitwise identical either way), "shared_args" (final-state solves whose args are shared read them from the
- * kernel parameter block instead of per-lane registers: 1 [default] / 0; bitwise identical results). */
+ * kernel parameter block instead of per-lane registers: 1 [default] / 0; bitwise identical with strict FP, within FMA-contraction
+ * noise in the production build). */
 int      cyrk_b200_set_option(const char* name, int value);
 /* FP64 FMA throughput probe (dependent-free DFMA streams on every SM): returns TFLOP/s. */
 double   cyrk_b200_measure_fp64_tflops(int device);

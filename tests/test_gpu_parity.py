@@ -210,6 +210,54 @@ def test_results_do_not_depend_on_scheduling():
             assert np.array_equal(a, b, equal_nan=True)
 
 
+def test_shared_args_in_the_parameter_block_are_bitwise_equal_to_per_lane_args():
+    """Final-state solves whose args are shared read them from the kernel parameter block (VAR_LEAN_SHARED, option
+    shared_args = 1, the default); per-lane registers with shared_args = 0 and with the same blob repeated per trajectory.
+    Same operations on the same values: with -fmad=false (strict_fp) every output is bitwise equal, for host and device inputs
+    and a zero-padded blob; in the production build the two kernels are separate compilations whose FMA contraction may differ
+    (Lorenz/DOP853 does), so there the step counts agree on >= 99.9 % of the batch and the states within 10 rtol / 10 atol."""
+    import torch
+    rng = np.random.default_rng(11)
+    B = 6000
+    y0 = np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)
+    yl = rng.uniform(1.0, 8.0, (B, 3))
+    cases = [("lotkavolterra", y0, [1.5, 1, 3, 1]), ("lorenz", yl, [10.0, 28.0, 8 / 3]), ("pendulum", y0 * 0.05, [1.0, 1.0, 9.81, 0.0, 0.0])]
+    names = ("status", "size", "steps_taken", "n_rejected", "nfev", "t_last", "y_last")
+    try:
+        for rhs, yy, args in cases:
+            for method, strict in [(m, st) for m in ("RK23", "RK45", "DOP853") for st in (True, False)]:
+                kw = dict(method=method, rtol=1e-6, atol=1e-9, store="final", strict_fp=strict)
+                outs = []
+                for shared_opt, a in ((1, args), (0, args), (1, np.tile(np.asarray(args, dtype=np.float64), (len(yy), 1)))):
+                    c.lib().cyrk_b200_set_option(b"shared_args", shared_opt)
+                    r = c.cysolve_ivp_batch(rhs, (0, 5.0), yy, args=a, **kw)
+                    outs.append([np.array(getattr(r, n)) for n in names])
+                c.lib().cyrk_b200_set_option(b"shared_args", 1)
+                rd = c.cysolve_ivp_batch(rhs, torch.tensor([0.0, 5.0], dtype=torch.float64, device="cuda"), torch.from_numpy(yy).cuda(),
+                                         args=torch.tensor(args, dtype=torch.float64, device="cuda"), **kw)
+                outs.append([torch.as_tensor(getattr(rd, n), device="cuda").cpu().numpy() for n in names])
+                assert (outs[0][0] == 1).all()
+                for o in outs[1:]:
+                    if strict:
+                        for n, x, y in zip(names, outs[0], o):
+                            assert np.array_equal(x, y, equal_nan=True), (rhs, method, n)
+                    else:
+                        assert np.array_equal(outs[0][0], o[0])
+                        assert (outs[0][2] == o[2]).mean() >= 0.999 and (outs[0][3] == o[3]).mean() >= 0.999, (rhs, method)
+                        same = outs[0][2] == o[2]
+                        assert np.all(np.abs(outs[0][6] - o[6])[same] <= (10 * 1e-6 * np.abs(o[6]) + 10 * 1e-9)[same]), (rhs, method)
+        # a short blob is zero padded in both paths (the reference copies whatever bytes it is given, cysolve.cpp:33-52)
+        outs = []
+        for shared_opt in (1, 0):
+            c.lib().cyrk_b200_set_option(b"shared_args", shared_opt)
+            r = c.cysolve_ivp_batch("lotkavolterra", (0, 3.0), y0[:500], method="RK45", args=[1.5, 1, 3], rtol=1e-6, atol=1e-9, store="final",
+                                    strict_fp=True)
+            outs.append((np.array(r.status), np.array(r.y_last)))
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1], equal_nan=True)
+    finally:
+        c.lib().cyrk_b200_set_option(b"shared_args", 1)
+
+
 def test_identical_trajectories_are_identical():
     """50 copies of one problem (test_c_parallel.py): every copy bitwise equal."""
     y0 = np.tile([10.0, 5.0], (50, 1))
