@@ -91,6 +91,7 @@ static int g_opt_cta_smem_vecs = -1;  // CTA path: working vectors kept in share
 static int g_opt_cta_block = 0;       // CTA path: threads per CTA (0 = by n_y)
 static int g_opt_pipe_taper = 1;       // pipelined host-I/O path: short first / last chunks
 static int g_opt_pipe_chunk = 1 << 20; // pipelined host-I/O path: trajectories per chunk (at most 32 chunks)
+static int g_opt_pipe_min = 1 << 18;   // pipelined host-I/O path: smallest batch that takes it (0 = never)
 static int g_opt_cta_kernel = 0;      // CTA path: 0 = pick (register-resident kernel where it is faster), 1 = always the
                                       // shared-memory/slab kernel, 2 = the register-resident kernel whenever n_y <= 4096
 static int g_opt_shared_args = 1;     // shared args through the kernel parameter block (VAR_LEAN_SHARED); 0 = per-lane registers
@@ -184,6 +185,11 @@ struct Handle {
     float kernel_ms = 0.f, total_ms = 0.f;
     unsigned launches = 0;
     size_t h2d_bytes = 0, d2h_bytes = 0;
+    // Per-trajectory result arrays whose host mirror is current.  A solve copies back what every caller reads (status,
+    // steps_taken, y_last; `size` where it decides about a re-run); the others stay in the device arena until their getter
+    // is called (cyrk_b200_get_*_ptr are pull-based like the reference's cysolver_get_*, numba_c_api_.cpp:91-213).
+    unsigned host_valid = 0;
+    size_t lazy_d2h_bytes = 0;
 
     int bind(int dev)
     {
@@ -203,6 +209,8 @@ struct Handle {
     }
     void destroy_cuda()
     {
+        int prev_dev = -1;
+        if (cudaGetDevice(&prev_dev) != cudaSuccess) { cudaGetLastError(); prev_dev = -1; }
         if (device >= 0) cudaSetDevice(device);
         DevBuf* dbs[] = {&d_y0, &d_args, &d_tspan, &d_teval, &d_queue, &d_status, &d_size, &d_steps, &d_nrej, &d_nfev,
                          &d_tlast, &d_ylast, &d_trows, &d_yrows, &d_dense_t, &d_dense_state, &d_dense_count, &d_ev_t,
@@ -225,6 +233,7 @@ struct Handle {
         ev_begin = ev_k0 = ev_k1 = ev_end = nullptr;
         stream = s_h2d = s_d2h = s_comp2 = nullptr;
         device = -1;
+        if (prev_dev >= 0) cudaSetDevice(prev_dev);
     }
     int events(size_t n)
     {
@@ -237,6 +246,38 @@ struct Handle {
     }
     ~Handle() { destroy_cuda(); }
 };
+
+// Every entry point that binds a device restores the caller's current device on the way out (a handle may be freed by a
+// garbage collector at any time; a multi-GPU process must not find its current device changed behind its back).
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+enum HostArr : int { HA_STATUS = 0, HA_SIZE, HA_STEPS, HA_NREJ, HA_NFEV, HA_TLAST, HA_YLAST, HA_COUNT };
+
+// Host (pinned) copy of one per-trajectory result array, fetched from the device arena on first use.
+static const void* host_array(Handle* h, int which)
+{
+    DevBuf* d[HA_COUNT] = {&h->d_status, &h->d_size, &h->d_steps, &h->d_nrej, &h->d_nfev, &h->d_tlast, &h->d_ylast};
+    PinBuf* p[HA_COUNT] = {&h->h_status, &h->h_size, &h->h_steps, &h->h_nrej, &h->h_nfev, &h->h_tlast, &h->h_ylast};
+    if (h->device_io) return d[which]->p;
+    if (!(h->host_valid & (1u << which)) && h->solved) {
+        const size_t per = which == HA_YLAST ? h->ndy * 8 : which == HA_TLAST ? 8 : 4;
+        const size_t bytes = h->n_traj * per;
+        DeviceGuard g;
+        if (cudaSetDevice(h->device) != cudaSuccess || p[which]->ensure(bytes) ||
+            cudaMemcpy(p[which]->p, d[which]->p, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();
+            if (g_last_error.empty()) set_error("lazy device-to-host copy of a result array failed");
+            return nullptr;
+        }
+        h->lazy_d2h_bytes += bytes;
+        h->host_valid |= 1u << which;
+    }
+    return p[which]->p;
+}
 
 // Built-in (precompiled) or user (NVRTC) kernels behind one interface.
 struct Dispatch {
@@ -360,7 +401,9 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
     const size_t args_stride = (size_t)pe->nargs_dbl * sizeof(double);
     // Chunk schedule: full chunks in the middle, a short one in front (the first copy-in is not overlapped with any
     // compute) and two short ones at the end (the last copy-out is not overlapped either).
-    const size_t chunk = std::max<size_t>((size_t)g_opt_pipe_chunk, (B + 31) / 32);
+    // chunk size: `pipe_chunk` (1 Mi: measured best at 8 Mi) for large batches, a quarter of the batch below 4 Mi so that
+    // a 256 Ki ... 2 Mi batch still overlaps its copies with the solve; never more than 32 chunks
+    const size_t chunk = std::max<size_t>(std::min<size_t>((size_t)g_opt_pipe_chunk, ((B + 3) / 4 + 1023) / 1024 * 1024), (B + 31) / 32);
     std::vector<std::pair<size_t, size_t>> sched;          // (offset, count)
     {
         size_t off = 0;
@@ -376,9 +419,7 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
     if (h->events(4 * nchunk)) return -1;
     if (h->d_y0.ensure(B * NY * 8) || h->d_queue.ensure(8 * nchunk)) return -1;
     if (use_prep && h->d_prep.ensure(B * (NDY + 2) * 8)) return -1;
-    if (h->h_status.ensure(B * 4) || h->h_size.ensure(B * 4) || h->h_steps.ensure(B * 4) || h->h_nrej.ensure(B * 4) ||
-        h->h_nfev.ensure(B * 4) || h->h_tlast.ensure(B * 8) || h->h_ylast.ensure(B * NDY * 8))
-        return -1;
+    if (h->h_status.ensure(B * 4) || h->h_steps.ensure(B * 4) || h->h_ylast.ensure(B * NDY * 8)) return -1;
     const bool per_traj_args = a.n_args > 1 && pe->nargs_dbl > 0;
     const bool per_traj_span = a.n_t_span > 1;
     // shared inputs once, on the copy-in stream
@@ -453,9 +494,9 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
         // ---- copy out
         CU_TRY(cudaStreamWaitEvent(h->s_d2h, e_k1, 0));
 #define D2H(host, dev, T, per) CU_TRY(cudaMemcpyAsync(h->host.as<T>() + off * (per), h->dev.as<T>() + off * (per), n * (per) * sizeof(T), cudaMemcpyDeviceToHost, h->s_d2h)); h->d2h_bytes += n * (per) * sizeof(T)
-        D2H(h_status, d_status, int, 1); D2H(h_size, d_size, unsigned, 1); D2H(h_steps, d_steps, unsigned, 1);
-        D2H(h_nrej, d_nrej, unsigned, 1); D2H(h_nfev, d_nfev, unsigned, 1); D2H(h_tlast, d_tlast, double, 1);
-        D2H(h_ylast, d_ylast, double, NDY);
+        // what every caller reads: 8 + 8*NDY bytes per trajectory.  size (= steps + 1 here), n_rejected, nfev and t_last
+        // stay in the device arena until their getter asks for them (host_array).
+        D2H(h_ylast, d_ylast, double, NDY); D2H(h_status, d_status, int, 1); D2H(h_steps, d_steps, unsigned, 1);
 #undef D2H
     }
     CU_TRY(cudaEventRecord(h->ev_end, h->s_d2h));
@@ -469,6 +510,7 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
     h->kernel_ms = k;
     cudaEventElapsedTime(&h->total_ms, h->ev_begin, h->ev_end);
     h->row_cap = h->dense_cap = h->ev_cap = 0;
+    h->host_valid = (1u << HA_STATUS) | (1u << HA_STEPS) | (1u << HA_YLAST);
     return 0;
 }
 
@@ -558,7 +600,8 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     h->ny = NY; h->nx = NX; h->ndy = NDY; h->q_order = q_order;
     h->n_traj = B; h->n_events = a.n_events; h->n_t_eval = a.n_t_eval;
     h->dense_output = dense; h->device_io = device_io;
-    h->h2d_bytes = h->d2h_bytes = 0; h->launches = 0; h->kernel_ms = 0.f;
+    h->h2d_bytes = h->d2h_bytes = h->lazy_d2h_bytes = 0; h->launches = 0; h->kernel_ms = 0.f;
+    h->host_valid = 0;
 
     BatchParams p;
     memset(&p, 0, sizeof(p));
@@ -648,7 +691,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     if (pick_grid(two_pass ? VAR_STEPS : variant)) return -1;
 
     // ---- host buffers + final-state variant + a batch worth cutting up: pipelined copy/compute path
-    if (!device_io && (variant == VAR_LEAN || variant == VAR_LEAN_SHARED) && B >= (size_t(1) << 21))
+    if (!device_io && (variant == VAR_LEAN || variant == VAR_LEAN_SHARED) && g_opt_pipe_min > 0 && B >= (size_t)g_opt_pipe_min)
         return solve_lean_pipelined(h, a, pe, p, grid, block, use_prep, variant);
 
     // ---- inputs
@@ -756,6 +799,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             h->launches++;
             CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
             if (download(h, h->h_size, h->d_size, B * 4)) return -1;
+            h->host_valid |= 1u << HA_SIZE;
             CU_TRY(cudaStreamSynchronize(h->stream));
             { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; if (getenv("CYRK_B200_DEBUG")) fprintf(stderr, "[cyrk_b200] step-recording solve: %.3f ms\n", ms); }
             size_t mx = 0;
@@ -867,7 +911,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
 
         // counters come back first: they decide whether any arena overflowed
         const bool need_check = want_rows || dense || a.n_events;
-        if ((need_check || !device_io) && download(h, h->h_size, h->d_size, B * 4)) return -1;
+        if (need_check) { if (download(h, h->h_size, h->d_size, B * 4)) return -1; h->host_valid |= 1u << HA_SIZE; }
         if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
         if (a.n_events && download(h, h->h_ev_count, h->d_ev_count, B * a.n_events * 4)) return -1;
         if (!need_check) break;
@@ -909,9 +953,9 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     // ---- results to the host
     if (!device_io) {
         if (download(h, h->h_status, h->d_status, B * 4) || download(h, h->h_steps, h->d_steps, B * 4) ||
-            download(h, h->h_nrej, h->d_nrej, B * 4) || download(h, h->h_nfev, h->d_nfev, B * 4) ||
-            download(h, h->h_tlast, h->d_tlast, B * 8) || download(h, h->h_ylast, h->d_ylast, B * NDY * 8))
+            download(h, h->h_ylast, h->d_ylast, B * NDY * 8))
             return -1;
+        h->host_valid |= (1u << HA_STATUS) | (1u << HA_STEPS) | (1u << HA_YLAST);
         if (want_rows) {
             if (download(h, h->h_trows, h->d_trows, B * row_cap * 8) || download(h, h->h_yrows, h->d_yrows, B * row_cap * NDY * 8))
                 return -1;
@@ -949,7 +993,8 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     h->n_traj = B; h->n_events = a.n_events; h->n_t_eval = a.n_t_eval;
     h->dense_output = dense; h->device_io = device_io; h->cta_path = true;
     h->q_order = a.method == CYRK_METHOD_RK23 ? 3 : a.method == CYRK_METHOD_RK45 ? 4 : 7;
-    h->h2d_bytes = h->d2h_bytes = 0; h->launches = 0; h->kernel_ms = 0.f;
+    h->h2d_bytes = h->d2h_bytes = h->lazy_d2h_bytes = 0; h->launches = 0; h->kernel_ms = 0.f;
+    h->host_valid = 0;
 
     CtaParams p;
     memset(&p, 0, sizeof(p));
@@ -1126,7 +1171,7 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         }
         h->launches++;
         CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
-        if ((want_rows || !device_io) && download(h, h->h_size, h->d_size, B * 4)) return -1;
+        if (want_rows) { if (download(h, h->h_size, h->d_size, B * 4)) return -1; h->host_valid |= 1u << HA_SIZE; }
         if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
         if (a.n_events && download(h, h->h_ev_count, h->d_ev_count, B * a.n_events * 4)) return -1;
         CU_TRY(cudaStreamSynchronize(h->stream));
@@ -1145,9 +1190,9 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     h->row_cap = row_cap; h->dense_cap = dense_cap; h->ev_cap = ev_cap;
     if (!device_io) {
         if (download(h, h->h_status, h->d_status, B * 4) || download(h, h->h_steps, h->d_steps, B * 4) ||
-            download(h, h->h_nrej, h->d_nrej, B * 4) || download(h, h->h_nfev, h->d_nfev, B * 4) ||
-            download(h, h->h_tlast, h->d_tlast, B * 8) || download(h, h->h_ylast, h->d_ylast, B * N * 8))
+            download(h, h->h_ylast, h->d_ylast, B * N * 8))
             return -1;
+        h->host_valid |= (1u << HA_STATUS) | (1u << HA_STEPS) | (1u << HA_YLAST);
         if (want_rows && (download(h, h->h_trows, h->d_trows, B * row_cap * 8) || download(h, h->h_yrows, h->d_yrows, B * row_cap * N * 8)))
             return -1;
         if (a.n_events && (download(h, h->h_ev_t, h->d_ev_t, B * a.n_events * ev_cap * 8) ||
@@ -1179,9 +1224,36 @@ static int validate(const SolveArgs& a)
     if (a.n_args > 0 && a.args_len > 0 && !a.args) { set_error("args pointer is NULL"); return -1; }
     if (a.n_events > CYRK_MAX_EVENTS) { set_error("at most %d events are supported", CYRK_MAX_EVENTS); return -1; }
     if (a.n_events && !a.event_ids) { set_error("event_ids is NULL"); return -1; }
+    for (size_t e = 0; e < a.n_events; e++)        // (both solver paths: the CTA path dispatches before the thread path's checks)
+        if (a.event_ids[e] < 0 || (a.rhs_id < CYRK_RHS_USER_BASE && a.event_ids[e] >= EV_TABLE_SIZE)) { set_error("unknown event id %d", a.event_ids[e]); return -1; }
     if (a.n_t_eval && !a.t_eval) { set_error("t_eval is NULL"); return -1; }
     if (a.store_mode != CYRK_STORE_FINAL && a.store_mode != CYRK_STORE_ROWS) { set_error("unknown store_mode %d", a.store_mode); return -1; }
     if (a.max_step < 0.0) { set_error("max_step must be positive"); return -1; }
+    const bool device_io = (a.flags & CYRK_FLAG_DEVICE_IO) != 0;
+    // t_span: finite, and -- because t_eval is shared -- one direction for the whole batch.  (Device-resident t_span is
+    // checked where the shim reads its first pair; NaN there gives every trajectory status -54 on its first attempt.)
+    bool fwd0 = true;
+    if (!device_io) {
+        for (size_t i = 0; i < a.n_t_span; i++) {
+            if (!std::isfinite(a.t_span[2 * i]) || !std::isfinite(a.t_span[2 * i + 1])) {
+                set_error("t_span[%zu] = (%g, %g) is not finite", i, a.t_span[2 * i], a.t_span[2 * i + 1]);
+                return -1;
+            }
+            const bool fwd = (a.t_span[2 * i + 1] - a.t_span[2 * i]) >= 0.0;
+            if (i == 0) fwd0 = fwd;
+            else if (a.n_t_eval && fwd != fwd0) {
+                set_error("t_eval is shared by the batch: every t_span must integrate in the same direction");
+                return -1;
+            }
+        }
+    }
+    for (size_t i = 0; i < a.n_t_eval; i++) {
+        if (!std::isfinite(a.t_eval[i])) { set_error("t_eval[%zu] = %g is not finite", i, a.t_eval[i]); return -1; }
+        if (i > 0 && !device_io && (fwd0 ? (a.t_eval[i] < a.t_eval[i - 1]) : (a.t_eval[i] > a.t_eval[i - 1]))) {
+            set_error("t_eval must be ordered in the direction of integration (t_eval[%zu] = %g follows %g)", i, a.t_eval[i], a.t_eval[i - 1]);
+            return -1;
+        }
+    }
     return 0;
 }
 
@@ -1196,6 +1268,7 @@ static int solve_impl(Handle* h, const SolveArgs& a)
         return -1;
     }
     if (a.device < 0 || a.device >= ndev) { set_error("device %d out of range (%d devices)", a.device, ndev); return -1; }
+    DeviceGuard guard;
     if (h->bind(a.device)) return -1;
     registry_init();
     const int fp = (a.flags & CYRK_FLAG_STRICT_FP) ? FP_STRICT : FP_FAST;
@@ -1224,8 +1297,6 @@ static int solve_impl(Handle* h, const SolveArgs& a)
         set_error("args blob of %zu bytes exceeds the %d bytes right-hand side %d reads", a.args_len, pe->nargs_dbl * 8, a.rhs_id);
         return -1;
     }
-    for (size_t e = 0; e < a.n_events; e++)
-        if (a.event_ids[e] < 0 || (a.rhs_id < CYRK_RHS_USER_BASE && a.event_ids[e] >= EV_TABLE_SIZE)) { set_error("unknown event id %d", a.event_ids[e]); return -1; }
     if (solve_thread_path(h, a, pe)) return -1;
     h->solved = true;
     return 0;
@@ -1331,6 +1402,12 @@ void cyrk_b200_status_message(int code, char* buffer, size_t max_len)
     case -7: m = "Error when accessing or modifying one or more attributes/properties."; break;
     case -8: m = "A bounds error was encountered."; break;
     case -9: m = "A required function or method argument was not set."; break;
+    // -10, -30, -31 and -60 have no entry in the reference's table (its flat API answers UNKNOWN_ERROR, its
+    // Python layer's map::at throws); this library does emit -10 (call_vectorize), -30 and -31 (event root search)
+    case -10: m = "A function or method argument is out of range or otherwise invalid."; break;
+    case -30: m = "Root finding failed: the function has the same sign at both ends of the bracket."; break;
+    case -31: m = "Root finding failed: the maximum number of iterations was reached without convergence."; break;
+    case -60: m = "Event setup failed."; break;
     case -20: m = "An object's additional setup function was not called before its methods were used."; break;
     case -21: m = "Can't call solution: Dense output was not saved."; break;
     case -22: m = "Error during setup: Provided configuration data does not make sense or is missing required parameters."; break;
@@ -1489,13 +1566,13 @@ int cyrk_b200_solve_batch_sharded(
 size_t cyrk_b200_get_n_traj(void* h) { return H(h)->n_traj; }
 size_t cyrk_b200_get_num_y(void* h) { return H(h)->ny; }
 size_t cyrk_b200_get_num_dy(void* h) { return H(h)->ndy; }
-const int32_t* cyrk_b200_get_status_ptr(void* h) { return PICK(h, d_status, h_status, int32_t); }
-const uint32_t* cyrk_b200_get_size_ptr(void* h) { return PICK(h, d_size, h_size, uint32_t); }
-const uint32_t* cyrk_b200_get_steps_taken_ptr(void* h) { return PICK(h, d_steps, h_steps, uint32_t); }
-const uint32_t* cyrk_b200_get_n_rejected_ptr(void* h) { return PICK(h, d_nrej, h_nrej, uint32_t); }
-const uint32_t* cyrk_b200_get_nfev_ptr(void* h) { return PICK(h, d_nfev, h_nfev, uint32_t); }
-const double* cyrk_b200_get_t_last_ptr(void* h) { return PICK(h, d_tlast, h_tlast, double); }
-const double* cyrk_b200_get_y_last_ptr(void* h) { return PICK(h, d_ylast, h_ylast, double); }
+const int32_t* cyrk_b200_get_status_ptr(void* h) { return static_cast<const int32_t*>(host_array(H(h), HA_STATUS)); }
+const uint32_t* cyrk_b200_get_size_ptr(void* h) { return static_cast<const uint32_t*>(host_array(H(h), HA_SIZE)); }
+const uint32_t* cyrk_b200_get_steps_taken_ptr(void* h) { return static_cast<const uint32_t*>(host_array(H(h), HA_STEPS)); }
+const uint32_t* cyrk_b200_get_n_rejected_ptr(void* h) { return static_cast<const uint32_t*>(host_array(H(h), HA_NREJ)); }
+const uint32_t* cyrk_b200_get_nfev_ptr(void* h) { return static_cast<const uint32_t*>(host_array(H(h), HA_NFEV)); }
+const double* cyrk_b200_get_t_last_ptr(void* h) { return static_cast<const double*>(host_array(H(h), HA_TLAST)); }
+const double* cyrk_b200_get_y_last_ptr(void* h) { return static_cast<const double*>(host_array(H(h), HA_YLAST)); }
 size_t cyrk_b200_get_row_capacity(void* h) { return H(h)->row_cap; }
 const double* cyrk_b200_get_t_ptr(void* h) { return H(h)->row_cap ? PICK(h, d_trows, h_trows, double) : nullptr; }
 const double* cyrk_b200_get_y_ptr(void* h) { return H(h)->row_cap ? PICK(h, d_yrows, h_yrows, double) : nullptr; }
@@ -1513,6 +1590,7 @@ int cyrk_b200_call_vectorize(void* hv, const double* t, size_t n_t, double* out,
     Handle* h = H(hv);
     if (!h || !h->solved) { set_error("handle holds no solution"); return -1; }
     if (!t || !out || !codes || n_t == 0) { set_error("t, out and codes are required"); return -1; }
+    DeviceGuard guard;
     CU_TRY(cudaSetDevice(h->device));
     const size_t B = h->n_traj, NDY = h->ndy;
     if (!h->dense_output) {
@@ -1606,6 +1684,7 @@ int cyrk_b200_ensemble_sums(void* hv, double* out)
     if (!out) { set_error("out is NULL"); return -1; }
     const int ndy = (int)h->ndy, nv = 2 * ndy + 1;
     if (nv > 256) { set_error("ensemble sums support num_dy <= 127"); return -1; }
+    DeviceGuard guard;
     CU_TRY(cudaSetDevice(h->device));
     const int block = 256, grid = std::max(1, std::min(device_sm_count(h->device) * 4, (int)((h->n_traj + block - 1) / block)));
     if (h->d_scratch.ensure((size_t)(grid + 1) * nv * 8)) return -1;
@@ -1625,6 +1704,7 @@ double cyrk_b200_get_total_ms(void* h) { return H(h)->total_ms; }
 unsigned cyrk_b200_get_launch_count(void* h) { return H(h)->launches; }
 size_t cyrk_b200_get_h2d_bytes(void* h) { return H(h)->h2d_bytes; }
 size_t cyrk_b200_get_d2h_bytes(void* h) { return H(h)->d2h_bytes; }
+size_t cyrk_b200_get_lazy_d2h_bytes(void* h) { return H(h)->lazy_d2h_bytes; }
 
 int cyrk_b200_set_option(const char* name, int value)
 {
@@ -1641,6 +1721,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
     if (!strcmp(name, "cta_kernel")) { g_opt_cta_kernel = value; return 0; }
     if (!strcmp(name, "pipe_taper")) { g_opt_pipe_taper = value; return 0; }
+    if (!strcmp(name, "pipe_min")) { g_opt_pipe_min = value; return 0; }
     if (!strcmp(name, "pipe_chunk")) { if (value < 1024) { set_error("pipe_chunk must be >= 1024"); return -1; } g_opt_pipe_chunk = value; return 0; }
     set_error("unknown option '%s'", name);
     return -1;
@@ -1648,6 +1729,7 @@ int cyrk_b200_set_option(const char* name, int value)
 
 int cyrk_b200_debug_sincos(const double* x, double* sin_out, double* cos_out, size_t n, int device)
 {
+    DeviceGuard guard;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_error("no CUDA device %d", device); return -1; }
     double *dx = nullptr, *ds = nullptr, *dc = nullptr;
     int rc = -1;
@@ -1665,6 +1747,7 @@ int cyrk_b200_debug_sincos(const double* x, double* sin_out, double* cos_out, si
 
 double cyrk_b200_measure_fp64_tflops(int device)
 {
+    DeviceGuard guard;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_error("no CUDA device %d", device); return -1.0; }
     const int sms = device_sm_count(device);
     const int block = 256, grid = sms * 8, iters = 1 << 15;

@@ -392,6 +392,13 @@ struct Cta2Solver {
 #pragma unroll
             for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) dst[i] = ybuf[i]; }
         }
+        if (p.n_t_eval > 0) {
+            // raw steps saved after t_eval has finished: keep y_last on the row t_last belongs to
+            // (without t_eval the final write-out stores it once)
+            double* yl = p.y_last + traj * n;
+#pragma unroll
+            for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) yl[i] = ybuf[i]; }
+        }
         t_last = t;
         size++;
     }

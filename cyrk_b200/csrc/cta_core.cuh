@@ -267,6 +267,10 @@ struct CtaSolver {
                 for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[i] = y[i];
             }
         }
+        if (p.n_t_eval > 0) {      // raw steps saved after t_eval has finished (quirk 6): y_last follows t_last
+            double* yl = p.y_last + traj * n;
+            for (unsigned i = threadIdx.x; i < n; i += blockDim.x) yl[i] = y[i];
+        }
         t_last = t;
         size++;
     }

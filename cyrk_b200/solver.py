@@ -116,13 +116,45 @@ def _is_cuda_tensor(x) -> bool:
     return hasattr(x, "is_cuda") and bool(getattr(x, "is_cuda")) and hasattr(x, "data_ptr")
 
 
-def _np_view(ptr, shape, dtype):
+class _HandleBox:
+    """Owns one native result handle (cyrk_b200_free on collection).  Every array view a BatchResult hands out keeps a
+    reference to its box, so the pinned memory under a view outlives the BatchResult it came from; the box is freed
+    when the last result AND the last view are gone, or explicitly by ``close()``."""
+
+    def __init__(self, h):
+        self.h = h
+
+    def close(self):
+        if self.h:
+            _lib.lib().cyrk_b200_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _OwnedArray(np.ndarray):
+    """Zero-copy view onto pinned memory of a native handle; `_owner` (propagated to slices and reshapes) keeps the
+    handle alive.  Valid until the owning result is closed or handed to ``solution_reuse`` -- copy (``np.array(x)``) what
+    must survive that, exactly like the reference's reused CySolverResult (Documentation/CySolverResult_Reuses.md)."""
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._owner = getattr(obj, "_owner", None)
+
+
+def _np_view(ptr, shape, dtype, owner=None):
     n = int(np.prod(shape)) if len(shape) else 1
     if not ptr or n == 0:
         return np.empty(shape, dtype=dtype)
     ctype = {np.float64: C.c_double, np.int32: C.c_int32, np.uint32: C.c_uint32}[dtype]
-    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
-    return arr.reshape(shape)
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)).reshape(shape).view(_OwnedArray)
+    arr._owner = owner
+    return arr
 
 
 class TrajectoryView:
@@ -204,49 +236,93 @@ class TrajectoryView:
 
 
 class BatchResult:
-    """Owns the native result handle (device arena + pinned host mirrors) of one batch solve."""
+    """One batch solve: per-trajectory arrays + ``result[i]`` views with the WrapCySolverResult attributes.
+
+    The arrays are zero-copy views onto the pinned host mirrors of the native handle (device pointers wrapped in
+    :class:`DeviceArray` for device-resident results).  They are created on first access: ``status``, ``steps_taken`` and
+    ``y_last`` (and stored rows / events) were copied back by the solve itself, the other per-trajectory arrays
+    (``size``, ``n_rejected``, ``nfev``, ``t_last``) are fetched from the device arena when first asked for.
+    Lifetime: every view keeps the native handle alive; ``close()`` and passing the result as ``solution_reuse``
+    invalidate the result (further attribute access raises) and any view still held by the caller.
+    """
+
+    # name -> (getter, dtype, shape function of the result)
+    _ARRAYS = {
+        "status": ("cyrk_b200_get_status_ptr", np.int32, lambda r: (r.n_traj,)),
+        "size": ("cyrk_b200_get_size_ptr", np.uint32, lambda r: (r.n_traj,)),
+        "steps_taken": ("cyrk_b200_get_steps_taken_ptr", np.uint32, lambda r: (r.n_traj,)),
+        "n_rejected": ("cyrk_b200_get_n_rejected_ptr", np.uint32, lambda r: (r.n_traj,)),
+        "nfev": ("cyrk_b200_get_nfev_ptr", np.uint32, lambda r: (r.n_traj,)),
+        "t_last": ("cyrk_b200_get_t_last_ptr", np.float64, lambda r: (r.n_traj,)),
+        "y_last": ("cyrk_b200_get_y_last_ptr", np.float64, lambda r: (r.n_traj, r.num_dy)),
+        "t_rows": ("cyrk_b200_get_t_ptr", np.float64, lambda r: (r.n_traj, r.row_capacity)),
+        "y_rows": ("cyrk_b200_get_y_ptr", np.float64, lambda r: (r.n_traj, r.row_capacity, r.num_dy)),
+        "event_count": ("cyrk_b200_get_event_count_ptr", np.uint32, lambda r: (r.n_traj, r.num_events)),
+        "event_t": ("cyrk_b200_get_event_t_ptr", np.float64, lambda r: (r.n_traj, r.num_events, r.event_capacity)),
+        "event_y": ("cyrk_b200_get_event_y_ptr", np.float64,
+                    lambda r: (r.n_traj, r.num_events, r.event_capacity, r.num_dy)),
+        "event_terminate_index": ("cyrk_b200_get_event_terminate_index_ptr", np.int32, lambda r: (r.n_traj,)),
+        "num_interpolates": ("cyrk_b200_get_num_interpolates_ptr", np.uint32, lambda r: (r.n_traj,)),
+    }
 
     def __init__(self, handle, method: int, keep_inputs=(), device_io: bool = False):
         L = _lib.lib()
-        self._h = handle
+        self._box = handle if isinstance(handle, _HandleBox) else _HandleBox(handle)
+        self._cache = {}
         self._keep = keep_inputs
         self.method = method
         self.device_io = device_io
-        if device_io:
-            owner = self
+        h = self._box.h
+        self.n_traj = L.cyrk_b200_get_n_traj(h)
+        self.num_y = L.cyrk_b200_get_num_y(h)
+        self.num_dy = L.cyrk_b200_get_num_dy(h)
+        self.row_capacity = L.cyrk_b200_get_row_capacity(h)
+        self.num_events = L.cyrk_b200_get_num_events(h)
+        self.event_capacity = L.cyrk_b200_get_event_capacity(h) if self.num_events else 0
+        self.kernel_ms = L.cyrk_b200_get_kernel_ms(h)
+        self.total_ms = L.cyrk_b200_get_total_ms(h)
+        self.launches = L.cyrk_b200_get_launch_count(h)
+        self.h2d_bytes = L.cyrk_b200_get_h2d_bytes(h)
+        self.d2h_bytes = L.cyrk_b200_get_d2h_bytes(h)
 
-            def _np_view(ptr, shape, dtype):     # noqa: F811 -- device pointers: never dereference on the host
-                return DeviceArray(ptr, shape, dtype, owner)
+    @property
+    def _h(self):
+        if self._box is None or not self._box.h:
+            raise CyrkB200Error("this BatchResult was closed or handed to solution_reuse: its arrays are gone")
+        return self._box.h
+
+    def __getattr__(self, name):
+        spec = BatchResult._ARRAYS.get(name)
+        if spec is None:
+            raise AttributeError(name)
+        cache = self.__dict__.get("_cache")
+        if cache is None:
+            raise AttributeError(name)
+        if name in cache:
+            return cache[name]
+        getter, dtype, shape_of = spec
+        h = self._h
+        if name in ("t_rows", "y_rows") and not self.row_capacity:
+            val = None
+        elif name.startswith("event_") and not self.num_events:
+            raise AttributeError(f"{name}: the solve had no events")
         else:
-            _np_view = globals()["_np_view"]
-        self.n_traj = B = L.cyrk_b200_get_n_traj(handle)
-        self.num_y = L.cyrk_b200_get_num_y(handle)
-        self.num_dy = ndy = L.cyrk_b200_get_num_dy(handle)
-        self.status = _np_view(L.cyrk_b200_get_status_ptr(handle), (B,), np.int32)
-        self.size = _np_view(L.cyrk_b200_get_size_ptr(handle), (B,), np.uint32)
-        self.steps_taken = _np_view(L.cyrk_b200_get_steps_taken_ptr(handle), (B,), np.uint32)
-        self.n_rejected = _np_view(L.cyrk_b200_get_n_rejected_ptr(handle), (B,), np.uint32)
-        self.nfev = _np_view(L.cyrk_b200_get_nfev_ptr(handle), (B,), np.uint32)
-        self.t_last = _np_view(L.cyrk_b200_get_t_last_ptr(handle), (B,), np.float64)
-        self.y_last = _np_view(L.cyrk_b200_get_y_last_ptr(handle), (B, ndy), np.float64)
-        cap = L.cyrk_b200_get_row_capacity(handle)
-        self.row_capacity = cap
-        self.t_rows = _np_view(L.cyrk_b200_get_t_ptr(handle), (B, cap), np.float64) if cap else None
-        self.y_rows = _np_view(L.cyrk_b200_get_y_ptr(handle), (B, cap, ndy), np.float64) if cap else None
-        self.num_events = ne = L.cyrk_b200_get_num_events(handle)
-        if ne:
-            ec = L.cyrk_b200_get_event_capacity(handle)
-            self.event_count = _np_view(L.cyrk_b200_get_event_count_ptr(handle), (B, ne), np.uint32)
-            self.event_t = _np_view(L.cyrk_b200_get_event_t_ptr(handle), (B, ne, ec), np.float64)
-            self.event_y = _np_view(L.cyrk_b200_get_event_y_ptr(handle), (B, ne, ec, ndy), np.float64)
-            self.event_terminate_index = _np_view(L.cyrk_b200_get_event_terminate_index_ptr(handle), (B,), np.int32)
-        ni = L.cyrk_b200_get_num_interpolates_ptr(handle)
-        self.num_interpolates = _np_view(ni, (B,), np.uint32) if ni else None
-        self.kernel_ms = L.cyrk_b200_get_kernel_ms(handle)
-        self.total_ms = L.cyrk_b200_get_total_ms(handle)
-        self.launches = L.cyrk_b200_get_launch_count(handle)
-        self.h2d_bytes = L.cyrk_b200_get_h2d_bytes(handle)
-        self.d2h_bytes = L.cyrk_b200_get_d2h_bytes(handle)
+            ptr = getattr(_lib.lib(), getter)(h)
+            shape = shape_of(self)
+            if name == "num_interpolates" and not ptr:
+                val = None
+            elif not ptr and int(np.prod(shape)) > 0:
+                raise CyrkB200Error(_lib.last_error() or f"{getter} returned NULL")
+            elif self.device_io:
+                val = DeviceArray(ptr, shape, dtype, self._box)
+            else:
+                val = _np_view(ptr, shape, dtype, self._box)
+        cache[name] = val
+        return val
+
+    @property
+    def lazy_d2h_bytes(self):
+        return _lib.lib().cyrk_b200_get_lazy_d2h_bytes(self._h)
 
     @property
     def success(self):
@@ -284,16 +360,16 @@ class BatchResult:
             raise CyrkB200Error(_lib.last_error())
         return out[:self.num_dy], out[self.num_dy:2 * self.num_dy], int(out[-1])
 
-    def close(self):
-        if self._h:
-            _lib.lib().cyrk_b200_free(self._h)
-            self._h = None
+    def _release(self):
+        """Give up the native handle without freeing it (solution_reuse hands it to the next result)."""
+        box, self._box = self._box, None
+        self._cache = {}
+        return box
 
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+    def close(self):
+        box = self._release()
+        if box is not None:
+            box.close()
 
 
 def cysolve_ivp_batch(
@@ -445,15 +521,15 @@ def cysolve_ivp_batch(
         return [(int(bounds[r]), int(bounds[r + 1]), BatchResult(hs[r], method_int, keep_inputs=keep)) for r in range(nd)]
     if solution_reuse is not None:
         # CySolverResult reuse (Documentation/CySolverResult_Reuses.md): same arena, new problem
-        h = solution_reuse._h
-        solution_reuse._h = None
-        if L.cyrk_b200_solve_batch_noreturn(h, *call_args) != 0:
-            L.cyrk_b200_free(h)
+        _ = solution_reuse._h                   # raises if that result was already closed / reused
+        box = solution_reuse._release()         # the old result (and views taken from it) is invalid from here on
+        if L.cyrk_b200_solve_batch_noreturn(box.h, *call_args) != 0:
+            box.close()
             raise CyrkB200Error(_lib.last_error())
-    else:
-        h = L.cyrk_b200_solve_batch(*call_args)
-        if not h:
-            raise CyrkB200Error(_lib.last_error())
+        return BatchResult(box, method_int, keep_inputs=keep, device_io=device_io)
+    h = L.cyrk_b200_solve_batch(*call_args)
+    if not h:
+        raise CyrkB200Error(_lib.last_error())
     return BatchResult(h, method_int, keep_inputs=keep, device_io=device_io)
 
 

@@ -192,7 +192,11 @@ void* cyrk_b200_result_create(void);
 void  cyrk_b200_free(void* handle);                                   /* cysolver_free */
 
 /* ---- getters (host pointers valid until the next solve on the handle or cyrk_b200_free;
- *      with CYRK_FLAG_DEVICE_IO they are DEVICE pointers) ------------------------------------ */
+ *      with CYRK_FLAG_DEVICE_IO they are DEVICE pointers).  Pull-based like the reference's cysolver_get_*
+ *      (numba_c_api_.cpp:91-213): a solve copies back status, steps_taken and y_last (8 + 8*num_dy bytes per trajectory,
+ *      plus whatever rows / events were asked for); size, n_rejected, nfev and t_last stay in the device arena until
+ *      their getter is first called, which then performs one device-to-host copy (NULL + cyrk_b200_last_error() if
+ *      that copy fails). ------------------------------------------------------------------------ */
 size_t          cyrk_b200_get_n_traj(void* h);
 size_t          cyrk_b200_get_num_y(void* h);
 size_t          cyrk_b200_get_num_dy(void* h);
@@ -233,12 +237,14 @@ double   cyrk_b200_get_kernel_ms(void* h);      /* CUDA-event time of the solve 
 double   cyrk_b200_get_total_ms(void* h);       /* CUDA-event time H2D -> kernels -> D2H of the last call   */
 unsigned cyrk_b200_get_launch_count(void* h);   /* kernels launched by the last call                        */
 size_t   cyrk_b200_get_h2d_bytes(void* h);
-size_t   cyrk_b200_get_d2h_bytes(void* h);
+size_t   cyrk_b200_get_d2h_bytes(void* h);      /* copied inside the solve call                             */
+size_t   cyrk_b200_get_lazy_d2h_bytes(void* h); /* copied afterwards by getters (see above)                 */
 /* Tuning knobs (process-wide): "refill_min" (1..32), "block" (threads per CTA of the thread-per-trajectory kernels,
  * 0 = by occupancy), "ctas_per_sm" (0 = occupancy API), "prep" (start-up kernel: -1 auto / 0 / 1), "root_batch" (1..32),
  * "cta_kernel" (0 = register-resident CTA kernel where it applies, 1 = shared-memory/slab kernel), "cta_block",
  * "cta_smem_vecs" (slab kernel only), "pipe_chunk" (trajectories per chunk of the pipelined host-I/O path),
- * "pipe_taper" (short first/last chunks, 0/1), "two_pass" (dense_output / t_eval without events or extras: 1 = step-parallel
+ * "pipe_taper" (short first/last chunks, 0/1), "pipe_min" (smallest host-buffer final-state batch that takes the pipelined path;
+ * default 256 Ki, 0 = never), "two_pass" (dense_output / t_eval without events or extras: 1 = step-parallel
  * interpolants when dense_output is set [default], 2 = also for t_eval alone, 0 = always the per-trajectory kernel; the
  * results are bitwise identical either way), "shared_args" (final-state solves whose args are shared read them from the
  * kernel parameter block instead of per-lane registers: 1 [default] / 0; bitwise identical with strict FP, within FMA-contraction

@@ -52,6 +52,39 @@ def test_status_messages_match_reference_table():
     assert c.status_message(12345) == "UNKNOWN_ERROR"
 
 
+def test_every_status_code_the_library_can_emit_has_a_message():
+    """cyrk_defs.h `enum Status` is the set of codes device code writes; each one must come back with a text (the
+    reference's table has no entry for -10 / -30 / -31, which this library does emit)."""
+    src = open(os.path.join(ROOT, "cyrk_b200", "csrc", "cyrk_defs.h")).read()
+    body = src[src.index("enum Status"):]
+    body = body[:body.index("};")]
+    codes = [int(v) for v in re.findall(r"=\s*(-?\d+)", body)]
+    assert len(codes) >= 20 and -10 in codes and -30 in codes and -31 in codes
+    for code in codes + [-60]:
+        assert c.status_message(code) != "UNKNOWN_ERROR", code
+
+
+def test_non_finite_or_unordered_times_are_rejected_before_any_launch():
+    """A NaN in t_span / t_eval used to reach the kernels (out-of-bounds t_eval walk); validation runs before the
+    device is touched, so this also holds on a box without a GPU."""
+    y0 = np.ones((3, 2))
+    kw = dict(method="RK45", args=[1.5, 1, 3, 1])
+    with pytest.raises(c.CyrkB200Error, match="not finite"):
+        c.cysolve_ivp_batch("lotkavolterra", (float("nan"), 1.0), y0, **kw)
+    with pytest.raises(c.CyrkB200Error, match="not finite"):
+        c.cysolve_ivp_batch("lotkavolterra", (0.0, float("inf")), y0, **kw)
+    with pytest.raises(c.CyrkB200Error, match="not finite"):
+        c.cysolve_ivp_batch("lotkavolterra", (0.0, 1.0), y0, t_eval=[0.0, float("nan"), 1.0], **kw)
+    with pytest.raises(c.CyrkB200Error, match="ordered in the direction"):
+        c.cysolve_ivp_batch("lotkavolterra", (0.0, 1.0), y0, t_eval=[0.0, 0.5, 0.25], **kw)
+    with pytest.raises(c.CyrkB200Error, match="ordered in the direction"):
+        c.cysolve_ivp_batch("lotkavolterra", (1.0, 0.0), y0, t_eval=[0.0, 0.5, 1.0], **kw)
+    with pytest.raises(c.CyrkB200Error, match="same direction"):
+        c.cysolve_ivp_batch("lotkavolterra", np.array([[0.0, 1.0], [1.0, 0.0], [0.0, 1.0]]), y0, t_eval=[0.0, 0.5], **kw)
+    with pytest.raises(c.CyrkB200Error, match="unknown event id"):
+        c.cysolve_ivp_batch("largey", (0.0, 1.0), np.ones((2, 64)), args=[-0.5, 64.0], events=[c.Event(99)])
+
+
 def test_python_layer_errors_match_reference():
     """pysolver.pyx:83,257,262 -- raised before anything touches the device."""
     y0 = np.ones((3, 2))

@@ -332,24 +332,50 @@ def test_full_size_c1_properties():
     assert 195 < r.steps_taken.mean() < 225 and r.steps_taken.min() >= 100 and r.steps_taken.max() <= 260
 
 
-def test_pipelined_host_path_equals_device_resident_path():
-    """Batches >= 2 Mi with host buffers go through the chunked copy/compute pipeline; results must be bitwise the
-    same as the single-launch device-resident path (per-trajectory args and spans exercise every offset)."""
+@pytest.mark.parametrize("B", [(1 << 18) + 777, (1 << 21) + 12345], ids=["256Ki", "2Mi"])
+def test_pipelined_host_path_equals_device_resident_path(B):
+    """Final-state batches >= 256 Ki with host buffers go through the chunked copy/compute pipeline; results must be
+    bitwise the same as the single-launch device-resident path (per-trajectory args and spans exercise every offset).
+    size / n_rejected / nfev / t_last are not part of the solve's own device-to-host traffic: their getters fetch them."""
     import torch
     rng = np.random.default_rng(11)
-    B = (1 << 21) + 12345
     y0 = np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)
     args = np.stack([rng.uniform(1.4, 1.6, B), np.ones(B), np.full(B, 3.0), np.ones(B)], 1)
     ts = np.stack([np.zeros(B), rng.uniform(2.0, 4.0, B)], 1)
     kw = dict(method="RK45", rtol=1e-6, atol=1e-8, store="final")
     host = c.cysolve_ivp_batch("lotkavolterra", ts, y0, args=args, **kw)
-    assert host.launches >= 4                                   # chunked (prep + solve per chunk)
+    assert host.launches >= 4                                   # chunked (one solve [+ prep] per chunk)
+    assert host.d2h_bytes == B * (4 + 4 + 2 * 8) and host.lazy_d2h_bytes == 0
     dev = c.cysolve_ivp_batch("lotkavolterra", torch.from_numpy(ts).cuda(), torch.from_numpy(y0).cuda(),
                               args=torch.from_numpy(args).cuda(), **kw)
     for name in ("status", "size", "steps_taken", "n_rejected", "nfev", "t_last", "y_last"):
         d = torch.as_tensor(getattr(dev, name), device="cuda").cpu().numpy()
         assert np.array_equal(np.asarray(getattr(host, name)), d, equal_nan=True), name
     assert (host.status == 1).all() and np.array_equal(host.t_last, ts[:, 1])
+    assert host.lazy_d2h_bytes == B * (4 + 4 + 4 + 8)            # size, n_rejected, nfev, t_last came on demand
+
+
+def test_result_views_keep_the_native_handle_alive_and_closing_invalidates():
+    """arrays handed out by a BatchResult are views onto pinned memory of the native handle."""
+    import gc
+    y0 = np.tile([10.0, 5.0], (64, 1))
+    kw = dict(method="RK45", args=[1.5, 1, 3, 1], rtol=1e-7, atol=1e-9, store="final")
+    y = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, **kw).y_last     # the BatchResult itself is dropped here
+    gc.collect()
+    _ = [c.cysolve_ivp_batch("lotkavolterra", (0.0, 3.0), y0, **kw) for _ in range(4)]   # churn pinned allocations
+    assert np.allclose(y, [0.2872127983010663, 0.44977767381276684], rtol=1e-6)       # SURVEY 8c KAT, still readable
+    row0 = y[0]                                     # slices keep the owner too
+    del y
+    gc.collect()
+    assert np.allclose(row0, [0.2872127983010663, 0.44977767381276684], rtol=1e-6)
+    r = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, **kw)
+    r2 = c.cysolve_ivp_batch("lotkavolterra", (0.0, 5.0), y0, solution_reuse=r, **kw)
+    with pytest.raises(c.CyrkB200Error, match="closed or handed to solution_reuse"):
+        _ = r.y_last
+    assert (r2.status == 1).all()
+    r2.close()
+    with pytest.raises(c.CyrkB200Error, match="closed or handed to solution_reuse"):
+        _ = r2.status
 
 
 def test_interpolate_from_solution_list(oracle):
