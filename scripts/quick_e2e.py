@@ -1,21 +1,36 @@
-"""End-to-end (host pinned buffers) C5 timing vs the pipeline chunk size."""
+"""End-to-end (host pinned buffers) final-state timing vs batch size and pipeline settings (pipe_min / pipe_chunk)."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import cyrk_b200 as c
 import bench
-w = bench.WORKLOADS["C5"]; B = w["batch"]
-y0, args = bench.make_inputs(w, B, 100)
-y0p = torch.from_numpy(y0).pin_memory().numpy(); ap = torch.from_numpy(np.ascontiguousarray(args)).pin_memory().numpy()
-for chunk, taper in ((1 << 20, 0), (1 << 20, 1), (1 << 19, 1), (3 << 19, 1)):
-    c.lib().cyrk_b200_set_option(b"pipe_chunk", chunk); c.lib().cyrk_b200_set_option(b"pipe_taper", taper)
+w = bench.WORKLOADS["C5"]
+L = c.lib()
+kw = dict(method="RK45", rtol=1e-7, atol=1e-9, store="final")
+for B in (1 << 18, 1 << 20, 1 << 21, 1 << 23):
+    y0, args = bench.make_inputs(w, B, 100)
+    y0p = torch.from_numpy(y0).pin_memory().numpy(); ap = torch.from_numpy(np.ascontiguousarray(args)).pin_memory().numpy()
+    y0d = torch.from_numpy(y0).cuda(); ad = torch.from_numpy(args).cuda()
     res = None
-    for _ in range(2):
-        res = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0p, args=ap, method="RK45", rtol=1e-7, atol=1e-9, store="final", solution_reuse=res)
-    torch.cuda.synchronize(); t0 = time.perf_counter(); n = 5; dev = 0.0
-    for _ in range(n):
-        res = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0p, args=ap, method="RK45", rtol=1e-7, atol=1e-9, store="final", solution_reuse=res)
-        dev += res.total_ms; _ = float(res.y_last[0, 0])
-    torch.cuda.synchronize(); wall = (time.perf_counter() - t0) / n * 1e3
-    print(f"chunk={chunk} taper={taper} wall_ms={wall:.2f} device_total_ms={dev / n:.2f} launches={res.launches}", flush=True)
+    for _ in range(3):
+        res = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0d, args=ad, solution_reuse=res, **kw)
+    dev_ms = min(c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0d, args=ad, **kw).total_ms for _ in range(3))
     res.close()
+    print(f"B={B} device-resident total_ms={dev_ms:.3f}", flush=True)
+    cfgs = [(0, 1 << 20, 1), (1 << 18, 1 << 20, 1), (1 << 18, 1 << 20, 0), (1 << 18, 1 << 19, 1), (1 << 18, 1 << 18, 1), (1 << 18, 1 << 17, 1)]
+    for pmin, chunk, taper in cfgs:
+        L.cyrk_b200_set_option(b"pipe_min", pmin); L.cyrk_b200_set_option(b"pipe_chunk", chunk); L.cyrk_b200_set_option(b"pipe_taper", taper)
+        res = None
+        for _ in range(2):
+            res = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0p, args=ap, solution_reuse=res, **kw)
+        torch.cuda.synchronize(); n = 6; best = 1e9; tot = 0.0
+        for _ in range(n):
+            t0 = time.perf_counter()
+            res = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0p, args=ap, solution_reuse=res, **kw)
+            _ = float(res.y_last[0, 0])
+            dt = (time.perf_counter() - t0) * 1e3
+            best = min(best, dt); tot += dt
+        print(f"  B={B} pipe_min={pmin} chunk={chunk} taper={taper}: wall_ms mean={tot / n:.3f} best={best:.3f} device_total_ms={res.total_ms:.3f} "
+              f"launches={res.launches} d2h={res.d2h_bytes} -> {B / (tot / n) * 1e3:.3e} solves/s ({dev_ms / (tot / n):.2f} of device-resident)", flush=True)
+        res.close()
+    L.cyrk_b200_set_option(b"pipe_min", 1 << 18); L.cyrk_b200_set_option(b"pipe_chunk", 1 << 20); L.cyrk_b200_set_option(b"pipe_taper", 1)
