@@ -60,6 +60,8 @@ SIGNATURES = {
     "cyrk_b200_get_y_ptr": (C.c_void_p, [C.c_void_p]),
     "cyrk_b200_get_num_events": (C.c_size_t, [C.c_void_p]),
     "cyrk_b200_get_event_capacity": (C.c_size_t, [C.c_void_p]),
+    "cyrk_b200_get_event_offsets_ptr": (C.c_void_p, [C.c_void_p]),
+    "cyrk_b200_get_event_total": (C.c_size_t, [C.c_void_p]),
     "cyrk_b200_get_event_count_ptr": (C.c_void_p, [C.c_void_p]),
     "cyrk_b200_get_event_t_ptr": (C.c_void_p, [C.c_void_p]),
     "cyrk_b200_get_event_y_ptr": (C.c_void_p, [C.c_void_p]),

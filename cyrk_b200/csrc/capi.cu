@@ -96,6 +96,8 @@ static int g_opt_cta_kernel = 0;      // CTA path: 0 = pick (register-resident k
                                       // shared-memory/slab kernel, 2 = the register-resident kernel whenever n_y <= 4096
 static int g_opt_shared_args = 1;     // shared args through the kernel parameter block (VAR_LEAN_SHARED); 0 = per-lane registers
 static int g_opt_two_pass = 1;        // t_eval / dense_output without events or extras: step-parallel interpolants (0 = the one-pass kernel)
+static int g_opt_dense_store = 0;     // two-pass path with dense_output: 0 = the 40-byte step records are the dense store (sol(t)
+                                      // recomputes the step it needs), 1 = materialise every [y_old | Q] interpolant as well
 static int g_opt_events_variant = 1;  // events with store='final' and no t_eval / dense store: the VAR_EVENTS kernels (0 = VAR_FULL)
 static int g_opt_root_batch = 12;     // measured: 8..16 is the flat optimum on the C3 workload (profiles/r01_notes.md)
 static int g_opt_ctas_per_sm = 0;
@@ -163,6 +165,7 @@ struct Handle {
     size_t n_events = 0, n_t_eval = 0;
     size_t row_cap = 0, dense_cap = 0, ev_cap = 0;
     bool dense_output = false, device_io = false, solved = false, cta_path = false;
+    bool dense_from_steps = false;         // sol(t) rebuilds interpolants from the step records in d_st (two-pass path)
     size_t args_stride = 0;
     // device arena
     DevBuf d_y0, d_args, d_tspan, d_teval, d_queue;
@@ -171,7 +174,10 @@ struct Handle {
     DevBuf d_ev_t, d_ev_y, d_ev_count, d_ev_term;
     DevBuf d_q_t, d_q_out, d_q_code, d_scratch, d_prep, d_rtol, d_atol;
     DevBuf d_st;                            // step records of the two-pass t_eval / dense path
-    DevBuf d_ev_t2, d_ev_y2;                // re-packed event arenas
+    DevBuf d_ev_t2, d_ev_y2, d_ev_off, d_scan;   // packed (CSR) event lists: hits back to back + offsets
+    PinBuf h_ev_off;
+    bool ev_packed = false;                 // host mirrors of the event lists are CSR-packed (host-buffer solves on the thread path)
+    size_t ev_total = 0;                    // hits in the packed arrays
     // pinned host mirrors
     PinBuf h_status, h_size, h_steps, h_nrej, h_nfev, h_tlast, h_ylast;
     PinBuf h_trows, h_yrows, h_dense_count, h_ev_t, h_ev_y, h_ev_count, h_ev_term;
@@ -215,10 +221,10 @@ struct Handle {
         DevBuf* dbs[] = {&d_y0, &d_args, &d_tspan, &d_teval, &d_queue, &d_status, &d_size, &d_steps, &d_nrej, &d_nfev,
                          &d_tlast, &d_ylast, &d_trows, &d_yrows, &d_dense_t, &d_dense_state, &d_dense_count, &d_ev_t,
                          &d_ev_y, &d_ev_count, &d_ev_term, &d_q_t, &d_q_out, &d_q_code, &d_scratch, &d_prep, &d_rtol, &d_atol,
-                         &d_st, &d_ev_t2, &d_ev_y2};
+                         &d_st, &d_ev_t2, &d_ev_y2, &d_ev_off, &d_scan};
         for (DevBuf* b : dbs) b->release();
         PinBuf* pbs[] = {&h_status, &h_size, &h_steps, &h_nrej, &h_nfev, &h_tlast, &h_ylast, &h_trows, &h_yrows,
-                         &h_dense_count, &h_ev_t, &h_ev_y, &h_ev_count, &h_ev_term, &h_stage};
+                         &h_dense_count, &h_ev_t, &h_ev_y, &h_ev_count, &h_ev_term, &h_stage, &h_ev_off};
         for (PinBuf* b : pbs) b->release();
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_k0) cudaEventDestroy(ev_k0);
@@ -551,19 +557,72 @@ __global__ void teval_last_kernel(unsigned long long n_traj, const unsigned* __r
     }
 }
 
-// Event arenas are allocated for `expected_size` hits per event (default 64) but typically hold a handful: before they
-// cross PCIe they are re-packed to the largest count that occurred.
-__global__ void repack_events_kernel(unsigned long long n_lists, unsigned old_cap, unsigned new_cap, unsigned ndy,
-                                     const double* __restrict__ t_in, const double* __restrict__ y_in,
-                                     double* __restrict__ t_out, double* __restrict__ y_out)
+// Event lists are ragged (the reference keeps one std::vector per event, cysolution.cpp:423-448).  On the device every
+// (trajectory, event) list owns `ev_cap` slots (default 64) but typically holds a handful of hits, so before they cross PCIe
+// the lists are packed back to back (CSR): offsets[l] .. offsets[l+1] index the hits of list l = traj * n_events + e.
+// Exclusive prefix sum of the per-list counts: block sums -> serial scan of the (few thousand) block sums -> offsets.
+constexpr int SCAN_BLOCK = 256, SCAN_ITEMS = 16;
+__global__ void scan_block_sums_kernel(const unsigned* __restrict__ cnt, unsigned long long n, unsigned long long* __restrict__ bsum)
 {
-    const unsigned long long total = n_lists * new_cap;
+    __shared__ unsigned long long sh[SCAN_BLOCK / 32];
+    const unsigned long long base = ((unsigned long long)blockIdx.x * SCAN_BLOCK + threadIdx.x) * SCAN_ITEMS;
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < n) s += cnt[base + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < SCAN_BLOCK / 32; w++) t += sh[w];
+        bsum[blockIdx.x] = t;
+    }
+}
+__global__ void scan_block_offsets_kernel(unsigned long long* __restrict__ bsum, unsigned nb, unsigned long long* __restrict__ total_out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long run = 0;
+        for (unsigned b = 0; b < nb; b++) { const unsigned long long v = bsum[b]; bsum[b] = run; run += v; }
+        *total_out = run;
+    }
+}
+__global__ void scan_write_kernel(const unsigned* __restrict__ cnt, unsigned long long n, const unsigned long long* __restrict__ bsum,
+                                  unsigned long long* __restrict__ off)
+{
+    __shared__ unsigned long long sh[SCAN_BLOCK];
+    const unsigned long long base = ((unsigned long long)blockIdx.x * SCAN_BLOCK + threadIdx.x) * SCAN_ITEMS;
+    unsigned c[SCAN_ITEMS];
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) { c[i] = (base + i < n) ? cnt[base + i] : 0u; s += c[i]; }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < SCAN_BLOCK; o <<= 1) {             // inclusive Hillis-Steele scan of the thread totals
+        const unsigned long long v = (threadIdx.x >= (unsigned)o) ? sh[threadIdx.x - o] : 0ull;
+        __syncthreads();
+        sh[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned long long run = bsum[blockIdx.x] + sh[threadIdx.x] - s;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) off[base + i] = run; run += c[i]; }
+    if (base <= n && n < base + SCAN_ITEMS) off[n] = bsum[blockIdx.x] + sh[threadIdx.x];     // the thread whose range holds index n
+}
+__global__ void pack_events_kernel(unsigned long long n_lists, unsigned cap, unsigned used_cap, unsigned ndy,
+                                   const unsigned* __restrict__ cnt, const unsigned long long* __restrict__ off,
+                                   const double* __restrict__ t_in, const double* __restrict__ y_in,
+                                   double* __restrict__ t_out, double* __restrict__ y_out)
+{
+    const unsigned long long total = n_lists * used_cap;
     for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long l = idx / new_cap;
-        const unsigned long long src = l * old_cap + (idx - l * new_cap);
-        t_out[idx] = t_in[src];
-        for (unsigned i = 0; i < ndy; i++) y_out[idx * ndy + i] = y_in[src * ndy + i];
+        const unsigned long long l = idx / used_cap;
+        const unsigned j = (unsigned)(idx - l * used_cap);
+        if (j >= cnt[l]) continue;
+        const unsigned long long src = l * cap + j, dst = off[l] + j;
+        t_out[dst] = t_in[src];
+        for (unsigned i = 0; i < ndy; i++) y_out[dst * ndy + i] = y_in[src * ndy + i];
     }
 }
 
@@ -599,7 +658,8 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
 
     h->ny = NY; h->nx = NX; h->ndy = NDY; h->q_order = q_order;
     h->n_traj = B; h->n_events = a.n_events; h->n_t_eval = a.n_t_eval;
-    h->dense_output = dense; h->device_io = device_io;
+    h->dense_output = dense; h->device_io = device_io; h->dense_from_steps = false;
+    h->ev_packed = false; h->ev_total = 0;
     h->h2d_bytes = h->d2h_bytes = h->lazy_d2h_bytes = 0; h->launches = 0; h->kernel_ms = 0.f;
     h->host_valid = 0;
 
@@ -826,7 +886,9 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         dense_cap = dense ? scap : 0;
         StepDenseParams q;
         memset(&q, 0, sizeof(q));
+        const bool materialise = dense && g_opt_dense_store != 0;
         q.n_traj = B; q.step_cap = (unsigned)scap; q.step_threads = (unsigned)std::min((std::max<size_t>(1, p_mx) + 31) / 32 * 32, scap);
+        if (!materialise && !a.n_t_eval && !rows_are_steps) q.step_threads = 32;      // only the per-trajectory counters are left to write
         q.steps_taken = p.steps_taken;
         q.recs = p_steps.step_recs; q.rows_are_steps = rows_are_steps ? 1 : 0;
         q.args = p.args; q.args_stride = p.args_stride;
@@ -838,11 +900,18 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         }
         q.dense_output = dense ? 1 : 0;
         if (dense) {
-            if (h->d_dense_t.ensure(B * dense_cap * 8) ||
-                h->d_dense_state.ensure(B * dense_cap * NY * (q_order + 1) * 8) || h->d_dense_count.ensure(B * 4))
-                return -1;
-            q.dense_t = h->d_dense_t.as<double>(); q.dense_state = h->d_dense_state.as<double>();
+            // The step records pass A wrote are all sol(t) needs: the interpolant of a step is a pure function of
+            // (t_old, y_old, step), so it is rebuilt when it is queried (dense_eval_body) instead of being stored --
+            // Lorenz/DOP853: 40 bytes per step kept instead of 216 written.  Option dense_store = 1 materialises them.
+            if (h->d_dense_count.ensure(B * 4)) return -1;
             q.dense_count = h->d_dense_count.as<unsigned>(); q.dense_cap = (unsigned)dense_cap;
+            if (materialise) {
+                if (h->d_dense_t.ensure(B * dense_cap * 8) || h->d_dense_state.ensure(B * dense_cap * NY * (q_order + 1) * 8)) return -1;
+                q.dense_t = h->d_dense_t.as<double>(); q.dense_state = h->d_dense_state.as<double>();
+            } else {
+                h->d_dense_t.release(); h->d_dense_state.release();       // (a reused handle may still hold them)
+                h->dense_from_steps = true;
+            }
         }
         q.nfev = p.nfev;
         CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
@@ -884,9 +953,6 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             p.dense_cap = (unsigned)dense_cap;
         }
         if (a.n_events) {
-            // (a reused handle: the arenas were swapped with their smaller re-packed copies at the end of the last solve)
-            if (h->d_ev_t2.cap > h->d_ev_t.cap) std::swap(h->d_ev_t, h->d_ev_t2);
-            if (h->d_ev_y2.cap > h->d_ev_y.cap) std::swap(h->d_ev_y, h->d_ev_y2);
             if (h->d_ev_t.ensure(B * a.n_events * ev_cap * 8) || h->d_ev_y.ensure(B * a.n_events * ev_cap * NDY * 8) ||
                 h->d_ev_count.ensure(B * a.n_events * 4) || h->d_ev_term.ensure(B * 4))
                 return -1;
@@ -934,19 +1000,32 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         dense_cap = std::max(dense_cap, mx_dense);
         ev_cap = std::max(ev_cap, mx_ev);
     }
-    if (a.n_events && !device_io && std::max<size_t>(ev_used, 1) * 2 <= ev_cap) {
-        const size_t new_cap = std::max<size_t>(ev_used, 1);
-        if (h->d_ev_t2.ensure(B * a.n_events * new_cap * 8) || h->d_ev_y2.ensure(B * a.n_events * new_cap * NDY * 8)) return -1;
-        const unsigned long long total = (unsigned long long)B * a.n_events * new_cap;
-        const int rgrid = (int)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)device_sm_count(h->device) * 32);
-        repack_events_kernel<<<rgrid, 256, 0, h->stream>>>((unsigned long long)B * a.n_events, (unsigned)ev_cap, (unsigned)new_cap, (unsigned)NDY,
-                                                           h->d_ev_t.as<double>(), h->d_ev_y.as<double>(),
-                                                           h->d_ev_t2.as<double>(), h->d_ev_y2.as<double>());
+    h->ev_packed = false; h->ev_total = 0;
+    if (a.n_events && !device_io) {
+        // pack the ragged hit lists back to back before they cross PCIe (C3: ~13 hits per trajectory in 3 x 64 slots)
+        const unsigned long long NL = (unsigned long long)B * a.n_events;
+        const unsigned nb = (unsigned)((NL + (unsigned long long)SCAN_BLOCK * SCAN_ITEMS - 1) / ((unsigned long long)SCAN_BLOCK * SCAN_ITEMS)) + 1u;   // (+1: the block that owns index NL)
+        if (h->d_ev_off.ensure((NL + 1) * 8) || h->d_scan.ensure(((size_t)nb + 1) * 8) || h->h_ev_off.ensure((NL + 1) * 8)) return -1;
+        unsigned long long* bsum = h->d_scan.as<unsigned long long>();
+        scan_block_sums_kernel<<<nb, SCAN_BLOCK, 0, h->stream>>>(p.ev_count, NL, bsum);
+        scan_block_offsets_kernel<<<1, 32, 0, h->stream>>>(bsum, nb, bsum + nb);
+        scan_write_kernel<<<nb, SCAN_BLOCK, 0, h->stream>>>(p.ev_count, NL, bsum, h->d_ev_off.as<unsigned long long>());
         CU_TRY(cudaGetLastError());
-        h->launches++;
-        std::swap(h->d_ev_t, h->d_ev_t2);
-        std::swap(h->d_ev_y, h->d_ev_y2);
-        ev_cap = new_cap;
+        unsigned long long total = 0;
+        CU_TRY(cudaMemcpyAsync(&total, bsum + nb, 8, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        if (h->d_ev_t2.ensure(std::max<size_t>(total, 1) * 8) || h->d_ev_y2.ensure(std::max<size_t>(total, 1) * NDY * 8)) return -1;
+        if (total > 0) {
+            const unsigned used = (unsigned)std::max<size_t>(ev_used, 1);
+            const unsigned long long work = NL * used;
+            const int rgrid = (int)std::min<unsigned long long>((work + 255) / 256, (unsigned long long)device_sm_count(h->device) * 32);
+            pack_events_kernel<<<rgrid, 256, 0, h->stream>>>(NL, (unsigned)ev_cap, used, (unsigned)NDY, p.ev_count, h->d_ev_off.as<unsigned long long>(),
+                                                             h->d_ev_t.as<double>(), h->d_ev_y.as<double>(),
+                                                             h->d_ev_t2.as<double>(), h->d_ev_y2.as<double>());
+            CU_TRY(cudaGetLastError());
+        }
+        h->launches += 4;
+        h->ev_packed = true; h->ev_total = (size_t)total;
     }
     h->row_cap = row_cap; h->dense_cap = dense_cap; h->ev_cap = ev_cap;
 
@@ -961,8 +1040,9 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
                 return -1;
         }
         if (a.n_events) {
-            if (download(h, h->h_ev_t, h->d_ev_t, B * a.n_events * ev_cap * 8) ||
-                download(h, h->h_ev_y, h->d_ev_y, B * a.n_events * ev_cap * NDY * 8) ||
+            if (download(h, h->h_ev_off, h->d_ev_off, (B * a.n_events + 1) * 8) ||
+                download(h, h->h_ev_t, h->d_ev_t2, h->ev_total * 8) ||
+                download(h, h->h_ev_y, h->d_ev_y2, h->ev_total * NDY * 8) ||
                 download(h, h->h_ev_term, h->d_ev_term, B * 4))
                 return -1;
         }
@@ -991,7 +1071,8 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     if (N > 0x7fffffffu) { set_error("n_y too large"); return -1; }
     h->ny = N; h->nx = 0; h->ndy = N; h->q_order = 0;
     h->n_traj = B; h->n_events = a.n_events; h->n_t_eval = a.n_t_eval;
-    h->dense_output = dense; h->device_io = device_io; h->cta_path = true;
+    h->dense_output = dense; h->device_io = device_io; h->cta_path = true; h->dense_from_steps = false;
+    h->ev_packed = false; h->ev_total = 0;
     h->q_order = a.method == CYRK_METHOD_RK23 ? 3 : a.method == CYRK_METHOD_RK45 ? 4 : 7;
     h->h2d_bytes = h->d2h_bytes = h->lazy_d2h_bytes = 0; h->launches = 0; h->kernel_ms = 0.f;
     h->host_valid = 0;
@@ -1577,7 +1658,9 @@ size_t cyrk_b200_get_row_capacity(void* h) { return H(h)->row_cap; }
 const double* cyrk_b200_get_t_ptr(void* h) { return H(h)->row_cap ? PICK(h, d_trows, h_trows, double) : nullptr; }
 const double* cyrk_b200_get_y_ptr(void* h) { return H(h)->row_cap ? PICK(h, d_yrows, h_yrows, double) : nullptr; }
 size_t cyrk_b200_get_num_events(void* h) { return H(h)->n_events; }
-size_t cyrk_b200_get_event_capacity(void* h) { return H(h)->ev_cap; }
+size_t cyrk_b200_get_event_capacity(void* h) { return H(h)->ev_packed ? 0 : H(h)->ev_cap; }
+const uint64_t* cyrk_b200_get_event_offsets_ptr(void* h) { return (H(h)->n_events && H(h)->ev_packed) ? static_cast<const uint64_t*>(H(h)->h_ev_off.p) : nullptr; }
+size_t cyrk_b200_get_event_total(void* h) { return H(h)->ev_total; }
 const uint32_t* cyrk_b200_get_event_count_ptr(void* h) { return H(h)->n_events ? PICK(h, d_ev_count, h_ev_count, uint32_t) : nullptr; }
 const double* cyrk_b200_get_event_t_ptr(void* h) { return H(h)->n_events ? PICK(h, d_ev_t, h_ev_t, double) : nullptr; }
 const double* cyrk_b200_get_event_y_ptr(void* h) { return H(h)->n_events ? PICK(h, d_ev_y, h_ev_y, double) : nullptr; }
@@ -1653,6 +1736,7 @@ int cyrk_b200_call_vectorize(void* hv, const double* t, size_t n_t, double* out,
     q.dense_state = h->d_dense_state.as<double>();
     q.dense_count = h->d_dense_count.as<unsigned>();
     q.dense_cap = (unsigned)h->dense_cap;
+    if (h->dense_from_steps) { q.recs = h->d_st.as<double>(); q.steps_taken = h->d_steps.as<unsigned>(); }
     q.args = h->in_args;
     q.args_stride = (unsigned)h->args_stride;
     double* d_out;
@@ -1715,6 +1799,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "prep")) { g_opt_prep = value; return 0; }
     if (!strcmp(name, "root_batch")) { g_opt_root_batch = value; return 0; }
     if (!strcmp(name, "two_pass")) { g_opt_two_pass = value; return 0; }
+    if (!strcmp(name, "dense_store")) { g_opt_dense_store = value; return 0; }
     if (!strcmp(name, "shared_args")) { g_opt_shared_args = value; return 0; }
     if (!strcmp(name, "events_variant")) { g_opt_events_variant = value; return 0; }
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }

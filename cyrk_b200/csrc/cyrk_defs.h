@@ -129,6 +129,11 @@ struct DenseEvalParams {
     const double*   dense_state;
     const unsigned* dense_count;
     unsigned        dense_cap;
+    // interpolants kept as STEP RECORDS (two-pass path, see StepDenseParams): [n_traj][dense_cap][CYRK_STEP_REC_DOUBLES(NY)];
+    // the queried step is recomputed from (t_old, y_old, step) -- 40 bytes per step for Lorenz instead of a 216-byte
+    // [y_old | Q] record.  NULL = dense_t / dense_state hold materialised interpolants.
+    const double*   recs;
+    const unsigned* steps_taken;
     const char*   args;
     unsigned      args_stride;
     double*       out;           // [n_traj][n_query][NDY]
@@ -153,9 +158,9 @@ struct StepDenseParams {
     double*       t_rows;        // [n_traj][row_cap]       t_eval samples (row j = the j-th sample the run passes)
     double*       y_rows;        // [n_traj][row_cap][NY]
     unsigned      row_cap;
-    int           dense_output;
-    double*       dense_t;       // as in BatchParams
-    double*       dense_state;
+    int           dense_output;  // count interpolants / their right-hand-side evaluations like the reference does
+    double*       dense_t;       // as in BatchParams; NULL = do not materialise the interpolants: the step records
+    double*       dense_state;   // themselves are the dense store and sol(t) recomputes the step it needs
     unsigned*     dense_count;
     unsigned      dense_cap;
     unsigned*     nfev;          // += the interpolant's extra right-hand-side evaluations (DOP853), counted the reference's way

@@ -151,7 +151,7 @@ def _np_view(ptr, shape, dtype, owner=None):
     n = int(np.prod(shape)) if len(shape) else 1
     if not ptr or n == 0:
         return np.empty(shape, dtype=dtype)
-    ctype = {np.float64: C.c_double, np.int32: C.c_int32, np.uint32: C.c_uint32}[dtype]
+    ctype = {np.float64: C.c_double, np.int32: C.c_int32, np.uint32: C.c_uint32, np.uint64: C.c_uint64}[dtype]
     arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)).reshape(shape).view(_OwnedArray)
     arr._owner = owner
     return arr
@@ -206,6 +206,10 @@ class TrajectoryView:
         b = self._b
         if b.num_events == 0:
             return None
+        if b.events_packed:
+            off = b.event_offsets
+            return [np.array(b.event_t[off[self._i * b.num_events + e]:off[self._i * b.num_events + e + 1]])
+                    for e in range(b.num_events)]
         return [np.array(b.event_t[self._i, e, :b.event_count[self._i, e]]) for e in range(b.num_events)]
 
     @property
@@ -213,6 +217,10 @@ class TrajectoryView:
         b = self._b
         if b.num_events == 0:
             return None
+        if b.events_packed:
+            off = b.event_offsets
+            return [np.array(b.event_y[off[self._i * b.num_events + e]:off[self._i * b.num_events + e + 1], :]).T
+                    for e in range(b.num_events)]
         return [np.array(b.event_y[self._i, e, :b.event_count[self._i, e], :]).T for e in range(b.num_events)]
 
     @property
@@ -258,9 +266,12 @@ class BatchResult:
         "t_rows": ("cyrk_b200_get_t_ptr", np.float64, lambda r: (r.n_traj, r.row_capacity)),
         "y_rows": ("cyrk_b200_get_y_ptr", np.float64, lambda r: (r.n_traj, r.row_capacity, r.num_dy)),
         "event_count": ("cyrk_b200_get_event_count_ptr", np.uint32, lambda r: (r.n_traj, r.num_events)),
-        "event_t": ("cyrk_b200_get_event_t_ptr", np.float64, lambda r: (r.n_traj, r.num_events, r.event_capacity)),
+        # events_packed: hits of list l = traj * num_events + e are event_t[event_offsets[l]:event_offsets[l + 1]]
+        "event_offsets": ("cyrk_b200_get_event_offsets_ptr", np.uint64, lambda r: (r.n_traj * r.num_events + 1,)),
+        "event_t": ("cyrk_b200_get_event_t_ptr", np.float64,
+                    lambda r: (r.event_total,) if r.events_packed else (r.n_traj, r.num_events, r.event_capacity)),
         "event_y": ("cyrk_b200_get_event_y_ptr", np.float64,
-                    lambda r: (r.n_traj, r.num_events, r.event_capacity, r.num_dy)),
+                    lambda r: (r.event_total, r.num_dy) if r.events_packed else (r.n_traj, r.num_events, r.event_capacity, r.num_dy)),
         "event_terminate_index": ("cyrk_b200_get_event_terminate_index_ptr", np.int32, lambda r: (r.n_traj,)),
         "num_interpolates": ("cyrk_b200_get_num_interpolates_ptr", np.uint32, lambda r: (r.n_traj,)),
     }
@@ -279,6 +290,8 @@ class BatchResult:
         self.row_capacity = L.cyrk_b200_get_row_capacity(h)
         self.num_events = L.cyrk_b200_get_num_events(h)
         self.event_capacity = L.cyrk_b200_get_event_capacity(h) if self.num_events else 0
+        self.event_total = L.cyrk_b200_get_event_total(h) if self.num_events else 0
+        self.events_packed = bool(self.num_events) and self.event_capacity == 0 and not device_io
         self.kernel_ms = L.cyrk_b200_get_kernel_ms(h)
         self.total_ms = L.cyrk_b200_get_total_ms(h)
         self.launches = L.cyrk_b200_get_launch_count(h)

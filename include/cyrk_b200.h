@@ -212,10 +212,19 @@ const double*   cyrk_b200_get_t_ptr(void* h);             /* [n_traj][row_capaci
 const double*   cyrk_b200_get_y_ptr(void* h);             /* [n_traj][row_capacity][num_dy] (row-major by step,
                                                              like CySolverResult::solution) */
 size_t          cyrk_b200_get_num_events(void* h);
+/* Event hits.  The reference keeps one ragged list per event (CySolverResult::event_times / event_states,
+ * cysolution.cpp:423-448).  Two layouts:
+ *   packed (host-buffer solves on the thread-per-trajectory path; event_capacity == 0): the hits of list
+ *     l = traj * n_events + e are event_t[offsets[l] .. offsets[l+1]) and event_y[...][num_dy] -- lists packed back to
+ *     back on the device before they cross PCIe; offsets has n_traj * n_events + 1 entries, event_total hits in all;
+ *   padded (CYRK_FLAG_DEVICE_IO and the CTA-per-trajectory path; event_capacity > 0, offsets == NULL): every list owns
+ *     event_capacity slots of which event_count[traj][e] are filled. */
 size_t          cyrk_b200_get_event_capacity(void* h);
 const uint32_t* cyrk_b200_get_event_count_ptr(void* h);   /* [n_traj][n_events] */
-const double*   cyrk_b200_get_event_t_ptr(void* h);       /* [n_traj][n_events][event_capacity] */
-const double*   cyrk_b200_get_event_y_ptr(void* h);       /* [n_traj][n_events][event_capacity][num_dy] */
+const uint64_t* cyrk_b200_get_event_offsets_ptr(void* h); /* [n_traj * n_events + 1], packed layout only */
+size_t          cyrk_b200_get_event_total(void* h);       /* hits in the packed arrays */
+const double*   cyrk_b200_get_event_t_ptr(void* h);       /* packed: [event_total]; padded: [n_traj][n_events][event_capacity] */
+const double*   cyrk_b200_get_event_y_ptr(void* h);       /* packed: [event_total][num_dy]; padded: [...][event_capacity][num_dy] */
 const int32_t*  cyrk_b200_get_event_terminate_index_ptr(void* h); /* [n_traj], -1 = not terminated */
 size_t          cyrk_b200_get_num_interpolates_capacity(void* h);
 const uint32_t* cyrk_b200_get_num_interpolates_ptr(void* h);      /* [n_traj] (dense_output only) */
@@ -246,7 +255,8 @@ size_t   cyrk_b200_get_lazy_d2h_bytes(void* h); /* copied afterwards by getters 
  * "pipe_taper" (short first/last chunks, 0/1), "pipe_min" (smallest host-buffer final-state batch that takes the pipelined path;
  * default 256 Ki, 0 = never), "two_pass" (dense_output / t_eval without events or extras: 1 = step-parallel
  * interpolants when dense_output is set [default], 2 = also for t_eval alone, 0 = always the per-trajectory kernel; the
- * results are bitwise identical either way), "shared_args" (final-state solves whose args are shared read them from the
+ * results are bitwise identical either way), "dense_store" (step-parallel path with dense_output: 0 [default] = the step records
+ * are the dense store and sol(t) recomputes the step it needs, 1 = every interpolant is materialised as well), "shared_args" (final-state solves whose args are shared read them from the
  * kernel parameter block instead of per-lane registers: 1 [default] / 0; bitwise identical with strict FP, within FMA-contraction
  * noise in the production build). */
 int      cyrk_b200_set_option(const char* name, int value);

@@ -1,6 +1,6 @@
 # cyrk_b200.pxd -- Cython declarations of include/cyrk_b200.h (generated from the header; see INTEGRATION.md).
 # `cimport` users call these `nogil`, like cysolve_ivp (CyRK/cy/cysolver_api.pxd:385-407).
-from libc.stdint cimport int32_t, uint32_t
+from libc.stdint cimport int32_t, uint32_t, uint64_t
 
 cdef extern from "cyrk_b200.h" nogil:
     enum: CYRK_METHOD_RK23
@@ -69,6 +69,8 @@ cdef extern from "cyrk_b200.h" nogil:
     const double* cyrk_b200_get_y_ptr(void* h)
     size_t cyrk_b200_get_num_events(void* h)
     size_t cyrk_b200_get_event_capacity(void* h)
+    const uint64_t* cyrk_b200_get_event_offsets_ptr(void* h)
+    size_t cyrk_b200_get_event_total(void* h)
     const uint32_t* cyrk_b200_get_event_count_ptr(void* h)
     const double* cyrk_b200_get_event_t_ptr(void* h)
     const double* cyrk_b200_get_event_y_ptr(void* h)
