@@ -89,6 +89,31 @@ WORKLOADS = {
 }
 # what the default N=1 run adds to the headline line: (workload, steps)
 EXTRA_WORKLOADS = [("C1", 3), ("C2full", 3), ("C3full", 3), ("C4", 3), ("C4simple", 3)]
+# BASELINE sizes of configs[1] / configs[2] (4 Mi trajectories).  C2's t_eval samples are 32 KB per trajectory on the host:
+# the batch is the largest power of two whose rows fit 35 % of the host memory available right now (4 Mi needs 134 GB).
+FULL_BATCH = {"C2full": 4 * 1024 * 1024, "C3full": 4 * 1024 * 1024}
+
+
+def host_mem_available():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) * 1024
+    except Exception:
+        pass
+    return 64 << 30
+
+
+def full_batch(name):
+    """Per-GPU batch of a BASELINE config at its stated size, bounded by what this host can hold."""
+    b = FULL_BATCH.get(name)
+    if b is None:
+        return WORKLOADS[name]["batch"]
+    if name == "C2full":
+        per_traj = 1000 * 4 * 8
+        while b > 65536 and b * per_traj > 0.35 * host_mem_available():
+            b //= 2
+    return b
 # parity samples next to the headline one: workload -> trajectories
 PARITY_SAMPLES = {"C2full": 64 * 1024, "C3full": 64 * 1024, "C4": 64}
 
@@ -560,7 +585,8 @@ def main():
             wl = {}
             for name, k in EXTRA_WORKLOADS:
                 ww = dict(WORKLOADS[name])
-                _log(f"workload {name}")
+                ww["batch"] = full_batch(name)
+                _log(f"workload {name}, {ww['batch']} trajectories")
                 try:
                     mm = gpu_measure(c, torch, ww, ww["batch"], 100, local_rank, k, 3, barrier)
                     mm.pop("result").close()

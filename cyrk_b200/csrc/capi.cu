@@ -196,6 +196,21 @@ struct Handle {
     // is called (cyrk_b200_get_*_ptr are pull-based like the reference's cysolver_get_*, numba_c_api_.cpp:91-213).
     unsigned host_valid = 0;
     size_t lazy_d2h_bytes = 0;
+    // ---- streamed (chunked) solves: a batch whose rows / event lists / step records are produced chunk by chunk.  The
+    // parent handle owns the whole-batch inputs, per-trajectory results, step records and pinned host arrays; two
+    // sub-handles own one chunk-sized arena each (rows, event slots) and alternate, so chunk k+1 solves while chunk k's
+    // rows cross PCIe.  `force` is set on a sub-handle while it solves a chunk.
+    Handle* sub[2] = {nullptr, nullptr};
+    struct Force {
+        bool active = false;
+        size_t row_cap = 0;                // rows per trajectory of the parent's host layout (0 = not fixed yet: probe chunk)
+        size_t scap = 0;                   // step records per trajectory of the parent's record store (0 = not fixed yet)
+        double* recs = nullptr;            // where this chunk's step records go (parent's store); NULL = the sub's own buffer
+        unsigned long long ev_base = 0;    // offset of this chunk's first hit in the parent's packed event arrays
+        size_t need_row_cap = 0, need_scap = 0;    // out: capacity this chunk would have needed (set when it returns 1)
+    } force;
+    bool took_two_pass = false;            // out: the last solve ran the step-parallel path
+    size_t step_cap = 0;                   // out: step records per trajectory of that path
 
     int bind(int dev)
     {
@@ -250,7 +265,7 @@ struct Handle {
         }
         return 0;
     }
-    ~Handle() { destroy_cuda(); }
+    ~Handle() { delete sub[0]; delete sub[1]; sub[0] = sub[1] = nullptr; destroy_cuda(); }
 };
 
 // Every entry point that binds a device restores the caller's current device on the way out (a handle may be freed by a
@@ -588,7 +603,7 @@ __global__ void scan_block_offsets_kernel(unsigned long long* __restrict__ bsum,
     }
 }
 __global__ void scan_write_kernel(const unsigned* __restrict__ cnt, unsigned long long n, const unsigned long long* __restrict__ bsum,
-                                  unsigned long long* __restrict__ off)
+                                  unsigned long long* __restrict__ off, unsigned long long first)
 {
     __shared__ unsigned long long sh[SCAN_BLOCK];
     const unsigned long long base = ((unsigned long long)blockIdx.x * SCAN_BLOCK + threadIdx.x) * SCAN_ITEMS;
@@ -604,13 +619,13 @@ __global__ void scan_write_kernel(const unsigned* __restrict__ cnt, unsigned lon
         sh[threadIdx.x] += v;
         __syncthreads();
     }
-    unsigned long long run = bsum[blockIdx.x] + sh[threadIdx.x] - s;
+    unsigned long long run = first + bsum[blockIdx.x] + sh[threadIdx.x] - s;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) off[base + i] = run; run += c[i]; }
-    if (base <= n && n < base + SCAN_ITEMS) off[n] = bsum[blockIdx.x] + sh[threadIdx.x];     // the thread whose range holds index n
+    if (base <= n && n < base + SCAN_ITEMS) off[n] = first + bsum[blockIdx.x] + sh[threadIdx.x];     // the thread whose range holds index n
 }
 __global__ void pack_events_kernel(unsigned long long n_lists, unsigned cap, unsigned used_cap, unsigned ndy,
-                                   const unsigned* __restrict__ cnt, const unsigned long long* __restrict__ off,
+                                   const unsigned* __restrict__ cnt, const unsigned long long* __restrict__ off, unsigned long long first,
                                    const double* __restrict__ t_in, const double* __restrict__ y_in,
                                    double* __restrict__ t_out, double* __restrict__ y_out)
 {
@@ -620,7 +635,7 @@ __global__ void pack_events_kernel(unsigned long long n_lists, unsigned cap, uns
         const unsigned long long l = idx / used_cap;
         const unsigned j = (unsigned)(idx - l * used_cap);
         if (j >= cnt[l]) continue;
-        const unsigned long long src = l * cap + j, dst = off[l] + j;
+        const unsigned long long src = l * cap + j, dst = off[l] - first + j;      // (offsets are global, the output buffer is this chunk's)
         t_out[dst] = t_in[src];
         for (unsigned i = 0; i < ndy; i++) y_out[dst * ndy + i] = y_in[src * ndy + i];
     }
@@ -827,11 +842,15 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     }
 
     size_t row_cap = 0, dense_cap = 0, ev_cap = 0, ev_used = 0;
+    Handle::Force& force = h->force;            // (inactive unless this handle is solving one chunk of a streamed batch)
     if (want_rows) row_cap = a.n_t_eval ? a.n_t_eval : (a.expected_size ? a.expected_size : 256);
+    if (want_rows && force.active && force.row_cap) row_cap = force.row_cap;
     if (dense) dense_cap = a.expected_size ? a.expected_size + 1 : 257;
     if (a.n_events) ev_cap = a.expected_size ? a.expected_size : 64;
 
     size_t p_scap = a.expected_size ? a.expected_size + 1 : 257, p_mx = 0;
+    if (force.active && force.scap) p_scap = force.scap;
+    h->took_two_pass = two_pass;
     BatchParams p_steps;
     if (two_pass) {
         // ---- pass A: final-state solve that records (t, y, step) of every booked step
@@ -843,8 +862,9 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         const size_t RA = CYRK_STEP_REC_DOUBLES(NY);
         for (int pass = 0; pass < 2; pass++) {
             scap = (scap + 31) / 32 * 32;       // whole warps per trajectory in step_dense_kernel
-            if (h->d_st.ensure(B * scap * RA * 8)) return -1;
-            pa.t_rows = nullptr; pa.y_rows = nullptr; pa.step_recs = h->d_st.as<double>();
+            if (force.active && force.recs) pa.step_recs = force.recs;
+            else { if (h->d_st.ensure(B * scap * RA * 8)) return -1; pa.step_recs = h->d_st.as<double>(); }
+            pa.t_rows = nullptr; pa.y_rows = nullptr;
             pa.row_cap = (unsigned)scap;
             CU_TRY(cudaMemsetAsync(h->d_queue.p, 0, 8, h->stream));
             CU_TRY(cudaEventRecord(h->ev_k0, h->stream));
@@ -866,6 +886,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             { const unsigned* sz = h->h_size.as<unsigned>(); for (size_t i = 0; i < B; i++) mx = std::max<size_t>(mx, sz[i]); }
             p_mx = mx;
             if (mx <= scap) break;
+            if (force.active && force.scap) { force.need_scap = mx; return 1; }      // the parent re-plans the whole batch
             if (pass == 1) { set_error("internal: arena overflow after the exact-capacity re-run"); return -1; }
             if (!dense && !rows_are_steps) {
                 // t_eval only: the per-trajectory kernel needs no per-step storage at all.  When some trajectory takes so
@@ -874,12 +895,15 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
                 cudaMemGetInfo(&fr, &tot);
                 if ((double)B * (double)mx * (8.0 * RA) > 0.5 * (double)(fr + h->d_st.cap)) { two_pass = false; break; }
             }
-            scap = mx;      // deterministic re-run with the exact capacity
+            // deterministic re-run with the exact capacity (the probe chunk of a streamed batch leaves headroom: its
+            // capacity becomes the layout of every later chunk)
+            scap = (force.active && !force.scap) ? mx + mx / 16 + 8 : mx;
         }
-        if (!two_pass) { h->d_st.release(); h->kernel_ms = 0.f; if (pick_grid(variant)) return -1; }
+        if (!two_pass) { h->d_st.release(); h->kernel_ms = 0.f; h->took_two_pass = false; if (pick_grid(variant)) return -1; }
     }
     if (two_pass) {
         const size_t scap = p_scap;
+        h->step_cap = scap;
         const bool rows_are_steps = want_rows && a.n_t_eval == 0;
         // ---- pass B: one thread per (trajectory, booked step): interpolant, dense record, t_eval samples
         row_cap = rows_are_steps ? scap : (want_rows ? a.n_t_eval : 0);
@@ -994,14 +1018,15 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         const bool overflow = mx_rows > row_cap || mx_dense > dense_cap || mx_ev > ev_cap;
         ev_used = mx_ev;
         if (!overflow) break;
+        if (force.active && force.row_cap && mx_rows > row_cap) { force.need_row_cap = mx_rows; return 1; }
         if (pass == 1) { set_error("internal: arena overflow after the exact-capacity re-run"); return -1; }
         // deterministic re-run with exact capacities
-        row_cap = std::max(row_cap, mx_rows);
+        row_cap = std::max(row_cap, (force.active && !force.row_cap && mx_rows > row_cap) ? mx_rows + mx_rows / 16 + 8 : mx_rows);
         dense_cap = std::max(dense_cap, mx_dense);
         ev_cap = std::max(ev_cap, mx_ev);
     }
     h->ev_packed = false; h->ev_total = 0;
-    if (a.n_events && !device_io) {
+    if (a.n_events && (!device_io || force.active)) {
         // pack the ragged hit lists back to back before they cross PCIe (C3: ~13 hits per trajectory in 3 x 64 slots)
         const unsigned long long NL = (unsigned long long)B * a.n_events;
         const unsigned nb = (unsigned)((NL + (unsigned long long)SCAN_BLOCK * SCAN_ITEMS - 1) / ((unsigned long long)SCAN_BLOCK * SCAN_ITEMS)) + 1u;   // (+1: the block that owns index NL)
@@ -1009,7 +1034,8 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         unsigned long long* bsum = h->d_scan.as<unsigned long long>();
         scan_block_sums_kernel<<<nb, SCAN_BLOCK, 0, h->stream>>>(p.ev_count, NL, bsum);
         scan_block_offsets_kernel<<<1, 32, 0, h->stream>>>(bsum, nb, bsum + nb);
-        scan_write_kernel<<<nb, SCAN_BLOCK, 0, h->stream>>>(p.ev_count, NL, bsum, h->d_ev_off.as<unsigned long long>());
+        const unsigned long long ev_first = force.active ? force.ev_base : 0ull;
+        scan_write_kernel<<<nb, SCAN_BLOCK, 0, h->stream>>>(p.ev_count, NL, bsum, h->d_ev_off.as<unsigned long long>(), ev_first);
         CU_TRY(cudaGetLastError());
         unsigned long long total = 0;
         CU_TRY(cudaMemcpyAsync(&total, bsum + nb, 8, cudaMemcpyDeviceToHost, h->stream));
@@ -1019,7 +1045,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             const unsigned used = (unsigned)std::max<size_t>(ev_used, 1);
             const unsigned long long work = NL * used;
             const int rgrid = (int)std::min<unsigned long long>((work + 255) / 256, (unsigned long long)device_sm_count(h->device) * 32);
-            pack_events_kernel<<<rgrid, 256, 0, h->stream>>>(NL, (unsigned)ev_cap, used, (unsigned)NDY, p.ev_count, h->d_ev_off.as<unsigned long long>(),
+            pack_events_kernel<<<rgrid, 256, 0, h->stream>>>(NL, (unsigned)ev_cap, used, (unsigned)NDY, p.ev_count, h->d_ev_off.as<unsigned long long>(), ev_first,
                                                              h->d_ev_t.as<double>(), h->d_ev_y.as<double>(),
                                                              h->d_ev_t2.as<double>(), h->d_ev_y2.as<double>());
             CU_TRY(cudaGetLastError());
@@ -1054,6 +1080,210 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1);
         h->kernel_ms = ms;
     }
+    cudaEventElapsedTime(&h->total_ms, h->ev_begin, h->ev_end);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streamed solves: rows / t_eval samples / event lists / step records chunk by chunk.
+//
+// CySolverResult grows its storage as the integration proceeds and hands everything to the caller at the end
+// (cysolution.cpp:396-448); a batch of millions of trajectories cannot keep every row in HBM at once (BASELINE config 2:
+// 4 Mi x 1000 samples = 134 GB).  So the batch is cut into chunks: whole-batch inputs, the 44-byte per-trajectory results
+// and -- with dense_output -- the 40-byte step records stay on the device in the parent handle; two sub-handles own one
+// chunk-sized arena each and alternate, so while chunk k's rows cross PCIe into the parent's pinned arrays, chunk k+1 is
+// being solved.  Every chunk runs the unmodified single-batch code (solve_thread_path on device pointers), so results
+// are identical to the unchunked call by construction (tests/test_gpu_streaming.py).  The first chunk is a probe: it
+// fixes the row / record capacity of the host layout; a later chunk that needs more makes the whole batch re-plan.
+// Returns 0, -1, or 2 = "not streamable after all" (the caller falls back to the single-arena path).
+// ------------------------------------------------------------------------------------------------
+static int g_opt_stream_chunk = 0;       // trajectories per chunk (0 = by arena size)
+static int g_opt_stream = 1;             // 0 = never stream
+
+static size_t stream_chunk_for(const SolveArgs& a, const Dispatch* pe)
+{
+    if (!g_opt_stream || (a.flags & CYRK_FLAG_DEVICE_IO)) return 0;
+    const size_t B = a.n_traj, NY = pe->ny, NX = pe->nextra, NDY = NY + NX;
+    const bool want_rows = a.store_mode == CYRK_STORE_ROWS, dense = a.dense_output != 0;
+    if (!(want_rows || dense || a.n_events || a.n_t_eval)) return 0;         // final-state solves have their own pipeline
+    // a dense store must outlive its chunk: only the step-record form (two-pass path) does
+    if (dense && (a.n_events || NX || !g_opt_two_pass || (a.n_t_eval && (!want_rows || a.n_t_span > 1)))) return 0;
+    const size_t rows = want_rows ? (a.n_t_eval ? a.n_t_eval : (a.expected_size ? a.expected_size : 256)) : 0;
+    const size_t per_traj = rows * (1 + NDY) * 8 + a.n_events * (a.expected_size ? a.expected_size : 64) * (1 + NDY) * 8 +
+                            ((a.n_t_eval || dense) ? (size_t)(a.expected_size ? a.expected_size + 32 : 288) * CYRK_STEP_REC_DOUBLES(NY) * 8 : 0) + 64;
+    size_t chunk;
+    if (g_opt_stream_chunk > 0) chunk = (size_t)g_opt_stream_chunk;
+    else {
+        if ((double)B * (double)per_traj < 1073741824.0) return 0;           // < 1 GiB of arena: one launch
+        chunk = std::min<size_t>((size_t)(3221225472.0 / (double)per_traj), B / 4);
+        chunk = std::max<size_t>(chunk / 1024 * 1024, 16384);
+    }
+    return (B >= 2 * chunk) ? chunk : 0;
+}
+
+static int solve_thread_streamed(Handle* h, const SolveArgs& a, const Dispatch* pe, size_t chunk)
+{
+    const size_t B = a.n_traj, NY = pe->ny, NX = pe->nextra, NDY = NY + NX, E = a.n_events;
+    const bool want_rows = a.store_mode == CYRK_STORE_ROWS, dense = a.dense_output != 0;
+    const size_t args_stride = (size_t)pe->nargs_dbl * 8;
+    const bool per_args = a.n_args > 1 && pe->nargs_dbl > 0, per_span = a.n_t_span > 1;
+    const size_t RA = CYRK_STEP_REC_DOUBLES(NY);
+    const int q_order = a.method == CYRK_METHOD_RK23 ? 3 : a.method == CYRK_METHOD_RK45 ? 4 : 7;
+
+    h->ny = NY; h->nx = NX; h->ndy = NDY; h->q_order = q_order;
+    h->n_traj = B; h->n_events = E; h->n_t_eval = a.n_t_eval;
+    h->dense_output = dense; h->device_io = false; h->dense_from_steps = false;
+    h->ev_packed = false; h->ev_total = 0;
+    h->h2d_bytes = h->d2h_bytes = h->lazy_d2h_bytes = 0; h->launches = 0; h->kernel_ms = 0.f;
+    h->host_valid = 0;
+    for (int s = 0; s < 2; s++) {
+        if (!h->sub[s]) h->sub[s] = new Handle();
+        if (h->sub[s]->bind(a.device)) return -1;
+    }
+    auto sync_subs = [&]() -> int {
+        CU_TRY(cudaStreamSynchronize(h->sub[0]->stream));
+        CU_TRY(cudaStreamSynchronize(h->sub[1]->stream));
+        return 0;
+    };
+    CU_TRY(cudaEventRecord(h->ev_begin, h->stream));
+
+    // ---- whole-batch inputs, uploaded once; the chunk solves read them in place
+    if (upload(h, h->d_y0, a.y0, B * NY * 8)) return -1;
+    if (pe->nargs_dbl > 0) {
+        const size_t n_blobs = per_args ? B : 1;
+        if (a.args_len == args_stride && a.n_args >= 1) {
+            if (upload(h, h->d_args, a.args, n_blobs * args_stride)) return -1;
+        } else {                                                    // zero-pad every blob to the functor's size
+            if (h->h_stage.ensure(n_blobs * args_stride)) return -1;
+            char* st = h->h_stage.as<char>();
+            memset(st, 0, n_blobs * args_stride);
+            if (a.n_args >= 1)
+                for (size_t i = 0; i < n_blobs; i++) memcpy(st + i * args_stride, a.args + i * a.args_len, a.args_len);
+            if (upload(h, h->d_args, st, n_blobs * args_stride)) return -1;
+        }
+    } else if (h->d_args.ensure(8)) return -1;
+    if (upload(h, h->d_tspan, a.t_span, a.n_t_span * 16)) return -1;
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    h->in_y0 = h->d_y0.as<double>(); h->in_args = h->d_args.as<char>(); h->in_tspan = h->d_tspan.as<double>();
+    h->tspan_stride = per_span ? 2u : 0u; h->args_stride = per_args ? args_stride : 0;
+
+    // ---- whole-batch per-trajectory results (device) and their eager host mirrors
+    if (h->d_status.ensure(B * 4) || h->d_size.ensure(B * 4) || h->d_steps.ensure(B * 4) || h->d_nrej.ensure(B * 4) ||
+        h->d_nfev.ensure(B * 4) || h->d_tlast.ensure(B * 8) || h->d_ylast.ensure(B * NDY * 8))
+        return -1;
+    if (h->h_status.ensure(B * 4) || h->h_steps.ensure(B * 4) || h->h_ylast.ensure(B * NDY * 8) || h->h_size.ensure(B * 4)) return -1;
+    if (dense && (h->d_dense_count.ensure(B * 4) || h->h_dense_count.ensure(B * 4))) return -1;
+    if (E && (h->d_ev_count.ensure(B * E * 4) || h->d_ev_term.ensure(B * 4) || h->h_ev_count.ensure(B * E * 4) ||
+              h->h_ev_term.ensure(B * 4) || h->h_ev_off.ensure((B * E + 1) * 8)))
+        return -1;
+
+    // (pinned buffers that other chunks' copies may still be writing into are only replaced after both streams drained)
+    auto grow_pinned = [&](PinBuf& b, size_t need, size_t keep) -> int {
+        if (need <= b.cap) return 0;
+        if (sync_subs()) return -1;
+        PinBuf nb;
+        if (nb.ensure(need)) return -1;
+        if (keep && b.p) memcpy(nb.p, b.p, keep);
+        b.release();
+        b = nb;
+        return 0;
+    };
+
+    size_t row_cap = 0, scap = 0;
+    bool planned = false, use_recs = false;
+    const size_t nchunk = (B + chunk - 1) / chunk;
+    for (int plan = 0;; plan++) {
+        if (plan >= 8) { set_error("streamed solve: capacity re-planning did not converge"); return -1; }
+        bool replan = false;
+        unsigned long long ev_base = 0;
+        h->kernel_ms = 0.f; h->launches = 0; h->d2h_bytes = 0;
+        if (planned) {                                             // (a re-plan: the layout grew)
+            if (want_rows && (h->h_trows.ensure(B * row_cap * 8) || h->h_yrows.ensure(B * row_cap * NDY * 8))) return -1;
+            if (use_recs && h->d_st.ensure(B * scap * RA * 8)) return -1;
+        }
+        for (size_t c = 0; c < nchunk && !replan; c++) {
+            const size_t off = c * chunk, n = std::min(chunk, B - off);
+            Handle* s = h->sub[c & 1];
+            SolveArgs ac = a;
+            ac.n_traj = n;
+            ac.y0 = h->d_y0.as<double>() + off * NY;
+            ac.args = h->d_args.as<char>() + (per_args ? off * args_stride : 0);
+            ac.args_len = pe->nargs_dbl > 0 ? args_stride : 0;
+            ac.n_args = pe->nargs_dbl > 0 ? (per_args ? n : 1) : 0;
+            ac.t_span = h->d_tspan.as<double>() + (per_span ? 2 * off : 0);
+            ac.n_t_span = per_span ? n : 1;
+            ac.flags |= CYRK_FLAG_DEVICE_IO;
+            s->force = Handle::Force();
+            s->force.active = true;
+            s->force.ev_base = ev_base;
+            if (planned) {
+                s->force.row_cap = row_cap; s->force.scap = scap;
+                if (use_recs) s->force.recs = h->d_st.as<double>() + off * scap * RA;
+            }
+            const int rc = solve_thread_path(s, ac, pe);          // (returns with this chunk's kernels finished)
+            s->force.active = false;
+            if (rc < 0) { sync_subs(); return -1; }
+            if (rc == 1) {                                         // needs more rows / records than the plan has: re-plan
+                if (s->force.need_row_cap) row_cap = std::max(row_cap, s->force.need_row_cap + s->force.need_row_cap / 8 + 1);
+                if (s->force.need_scap) scap = std::max(scap, (s->force.need_scap + s->force.need_scap / 8 + 32) / 32 * 32);
+                if (want_rows && !a.n_t_eval && scap) row_cap = scap;      // (two-pass path without t_eval: the rows ARE the records)
+                replan = true;
+                break;
+            }
+            if (!planned) {
+                // probe chunk: its layout becomes the batch's
+                if (dense && !s->dense_from_steps) { sync_subs(); return 2; }     // dense store would not outlive the chunk
+                row_cap = s->row_cap;
+                scap = s->took_two_pass ? s->step_cap : 0;
+                use_recs = s->took_two_pass && dense;
+                if (want_rows && (h->h_trows.ensure(B * row_cap * 8) || h->h_yrows.ensure(B * row_cap * NDY * 8))) return -1;
+                if (use_recs) {
+                    if (h->d_st.ensure(B * scap * RA * 8)) return -1;
+                    CU_TRY(cudaMemcpyAsync(h->d_st.p, s->d_st.p, n * scap * RA * 8, cudaMemcpyDeviceToDevice, s->stream));
+                }
+                planned = true;
+            }
+            // ---- deliver this chunk (on ITS stream: the next solve on this sub-handle is ordered behind the copies)
+#define D2D(name, T, per) CU_TRY(cudaMemcpyAsync(h->name.as<T>() + off * (per), s->name.as<T>(), n * (per) * sizeof(T), cudaMemcpyDeviceToDevice, s->stream))
+#define D2H(host, dev, T, per) do { CU_TRY(cudaMemcpyAsync(h->host.as<T>() + off * (per), s->dev.as<T>(), n * (per) * sizeof(T), cudaMemcpyDeviceToHost, s->stream)); h->d2h_bytes += n * (per) * sizeof(T); } while (0)
+            D2D(d_status, int, 1); D2D(d_size, unsigned, 1); D2D(d_steps, unsigned, 1); D2D(d_nrej, unsigned, 1);
+            D2D(d_nfev, unsigned, 1); D2D(d_tlast, double, 1); D2D(d_ylast, double, NDY);
+            D2H(h_status, d_status, int, 1); D2H(h_steps, d_steps, unsigned, 1); D2H(h_ylast, d_ylast, double, NDY);
+            D2H(h_size, d_size, unsigned, 1);
+            if (dense) { D2D(d_dense_count, unsigned, 1); D2H(h_dense_count, d_dense_count, unsigned, 1); }
+            if (want_rows) { D2H(h_trows, d_trows, double, row_cap); D2H(h_yrows, d_yrows, double, row_cap * NDY); }
+            if (E) {
+                const size_t tot = s->ev_total;
+                if (ev_base + tot > h->h_ev_t.cap / 8) {            // grow from what the chunks so far suggest
+                    const double per_traj = (double)(ev_base + tot) / (double)(off + n);
+                    const size_t want = std::max<size_t>((size_t)(per_traj * 1.25 * (double)B) + 1024, ev_base + tot);
+                    if (grow_pinned(h->h_ev_t, want * 8, ev_base * 8) || grow_pinned(h->h_ev_y, want * NDY * 8, ev_base * NDY * 8)) return -1;
+                }
+                D2D(d_ev_count, unsigned, E); D2D(d_ev_term, int, 1);
+                D2H(h_ev_count, d_ev_count, unsigned, E); D2H(h_ev_term, d_ev_term, int, 1);
+                CU_TRY(cudaMemcpyAsync(h->h_ev_off.as<unsigned long long>() + off * E, s->d_ev_off.p, (n * E + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
+                if (tot) {
+                    CU_TRY(cudaMemcpyAsync(h->h_ev_t.as<double>() + ev_base, s->d_ev_t2.p, tot * 8, cudaMemcpyDeviceToHost, s->stream));
+                    CU_TRY(cudaMemcpyAsync(h->h_ev_y.as<double>() + ev_base * NDY, s->d_ev_y2.p, tot * NDY * 8, cudaMemcpyDeviceToHost, s->stream));
+                }
+                h->d2h_bytes += (n * E + 1) * 8 + tot * (1 + NDY) * 8;
+                ev_base += tot;
+            }
+#undef D2D
+#undef D2H
+            h->kernel_ms += s->kernel_ms; h->launches += s->launches;
+        }
+        if (sync_subs()) return -1;
+        if (!replan) { h->ev_total = (size_t)ev_base; break; }
+    }
+    h->row_cap = want_rows ? row_cap : 0;
+    h->dense_cap = dense ? scap : 0;
+    h->ev_cap = 0; h->ev_packed = E > 0;
+    h->dense_from_steps = use_recs;
+    h->step_cap = scap;
+    h->host_valid = (1u << HA_STATUS) | (1u << HA_STEPS) | (1u << HA_YLAST) | (1u << HA_SIZE);
+    CU_TRY(cudaEventRecord(h->ev_end, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
     cudaEventElapsedTime(&h->total_ms, h->ev_begin, h->ev_end);
     return 0;
 }
@@ -1377,6 +1607,11 @@ static int solve_impl(Handle* h, const SolveArgs& a)
     if (a.n_args > 0 && a.args_len > (size_t)pe->nargs_dbl * 8) {
         set_error("args blob of %zu bytes exceeds the %d bytes right-hand side %d reads", a.args_len, pe->nargs_dbl * 8, a.rhs_id);
         return -1;
+    }
+    if (const size_t chunk = stream_chunk_for(a, pe)) {
+        const int rc = solve_thread_streamed(h, a, pe, chunk);
+        if (rc < 0) return -1;
+        if (rc == 0) { h->solved = true; return 0; }
     }
     if (solve_thread_path(h, a, pe)) return -1;
     h->solved = true;
@@ -1800,6 +2035,8 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "root_batch")) { g_opt_root_batch = value; return 0; }
     if (!strcmp(name, "two_pass")) { g_opt_two_pass = value; return 0; }
     if (!strcmp(name, "dense_store")) { g_opt_dense_store = value; return 0; }
+    if (!strcmp(name, "stream")) { g_opt_stream = value; return 0; }
+    if (!strcmp(name, "stream_chunk")) { g_opt_stream_chunk = value; return 0; }
     if (!strcmp(name, "shared_args")) { g_opt_shared_args = value; return 0; }
     if (!strcmp(name, "events_variant")) { g_opt_events_variant = value; return 0; }
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
