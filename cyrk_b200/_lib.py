@@ -76,6 +76,8 @@ SIGNATURES = {
     "cyrk_b200_get_h2d_bytes": (C.c_size_t, [C.c_void_p]),
     "cyrk_b200_get_d2h_bytes": (C.c_size_t, [C.c_void_p]),
     "cyrk_b200_get_lazy_d2h_bytes": (C.c_size_t, [C.c_void_p]),
+    "cyrk_b200_jit_compile": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint]),
+    "cyrk_b200_jit_cache_stats": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "cyrk_b200_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "cyrk_b200_measure_fp64_tflops": (C.c_double, [C.c_int]),
     "cyrk_b200_solve_batch_sharded": (C.c_int, [C.POINTER(C.c_int), C.c_size_t, C.POINTER(C.c_void_p), c_size_p] + _SOLVE_ARGS[:-1]),

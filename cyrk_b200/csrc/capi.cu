@@ -307,21 +307,35 @@ struct Dispatch {
     int device = 0;
     const ProblemEntry* pe = nullptr;       // null => user right-hand side
     int ny = 0, nextra = 0, nargs_dbl = 0;
-    const char* name(int method, int variant) const { return pe ? pe->solve[method - 3][variant].name : "user"; }
+    // Feature builds of the solve / prep kernels (per-trajectory tolerances): compiled on demand with NVRTC -- for the
+    // built-in problems too (jit_id: the problem registered as a run-time right-hand side) -- instead of doubling the
+    // number of precompiled instantiations for a rarely used option.
+    std::string jit_defs;
+    int jit_id = -1;
+    const char* name(int method, int variant) const { return (pe && jit_defs.empty()) ? pe->solve[method - 3][variant].name : (pe ? pe->struct_name : "user"); }
     cudaError_t occupancy(int method, int variant, int* ctas, int block) const
     {
-        if (pe) return pe->solve[method - 3][variant].occupancy(ctas, block);
-        return user_rhs_occupancy(rhs_id, method, variant, strict, device, ctas, block);
+        if (pe && jit_defs.empty()) return pe->solve[method - 3][variant].occupancy(ctas, block);
+        return user_rhs_occupancy(pe ? jit_id : rhs_id, method, variant, strict, device, ctas, block, jit_defs.c_str());
     }
     cudaError_t launch(int method, int variant, const BatchParams& p, int grid, int block, cudaStream_t s) const
     {
-        if (pe) return pe->solve[method - 3][variant].launch(p, grid, block, s);
-        return user_rhs_launch_solve(rhs_id, method, variant, strict, device, p, grid, block, s);
+        if (pe && jit_defs.empty()) return pe->solve[method - 3][variant].launch(p, grid, block, s);
+        return user_rhs_launch_solve(pe ? jit_id : rhs_id, method, variant, strict, device, p, grid, block, s, jit_defs.c_str());
     }
     cudaError_t prep(int method, const BatchParams& p, double* out, int grid, int block, cudaStream_t s) const
     {
-        if (pe) return pe->prep[method - 3](p, out, grid, block, s);
-        return user_rhs_launch_prep(rhs_id, method, strict, device, p, out, grid, block, s);
+        if (pe && jit_defs.empty()) return pe->prep[method - 3](p, out, grid, block, s);
+        return user_rhs_launch_prep(pe ? jit_id : rhs_id, method, strict, device, p, out, grid, block, s, jit_defs.c_str());
+    }
+    int use_feature(const char* defs)
+    {
+        jit_defs = defs;
+        if (pe) {
+            jit_id = builtin_jit_id(pe->struct_name, pe->ny, pe->nextra, pe->nargs_dbl);
+            if (jit_id < 0) { set_error("cannot register built-in problem %s for run-time compilation", pe->struct_name); return -1; }
+        }
+        return 0;
     }
     cudaError_t step_dense(int method, const StepDenseParams& p, int grid, int block, cudaStream_t s) const
     {
@@ -498,6 +512,7 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
         q.t_span = h->d_tspan.as<double>() + (per_traj_span ? off * 2 : 0);
         q.status = p.status + off; q.size = p.size + off; q.steps_taken = p.steps_taken + off;
         q.n_rejected = p.n_rejected + off; q.nfev = p.nfev + off; q.t_last = p.t_last + off; q.y_last = p.y_last + off * NDY;
+        if (p.rtol_pt) { q.rtol_pt = p.rtol_pt + off * NY; q.atol_pt = p.atol_pt + off * NY; }
         q.queue = h->d_queue.as<unsigned long long>() + c;
         const int cgrid = (int)std::min<unsigned long long>((unsigned long long)grid, (n + block - 1) / block);
         CU_TRY(cudaStreamWaitEvent(sc, e_in, 0));
@@ -659,8 +674,10 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     // per-trajectory kernel is as fast and needs no per-step records (option two_pass = 2 forces it there as well).
     bool two_pass = g_opt_two_pass != 0 && variant == VAR_ROWS && NX == 0 && (dense || (a.n_t_eval > 0 && g_opt_two_pass == 2)) &&
                     (a.n_t_eval == 0 || want_rows);
+    const bool te_pt = a.n_t_eval > 0 && (a.flags & CYRK_FLAG_T_EVAL_PER_TRAJ) != 0;
+    const bool tol_pt = (a.flags & CYRK_FLAG_TOL_PER_TRAJ) != 0;
     if (two_pass && a.n_t_eval > 0) {
-        if (a.n_t_span > 1) two_pass = false;
+        if (a.n_t_span > 1 || te_pt) two_pass = false;      // (the step-parallel path ranks samples in ONE shared grid)
         else {
             double ts0[2];
             if (device_io) {
@@ -697,11 +714,22 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         }
         if (ok) variant = VAR_LEAN_SHARED;
     }
-    for (size_t i = 0; i < NY; i++) {
+    for (size_t i = 0; i < NY && !tol_pt; i++) {
         double r = a.rtols[a.n_rtols > 1 ? i : 0];
         if (r < 100.0 * std::numeric_limits<double>::epsilon()) r = 100.0 * std::numeric_limits<double>::epsilon();
         p.rtol[i] = r;
         p.atol[i] = a.atols[a.n_atols > 1 ? i : 0];
+    }
+    if (tol_pt) {
+        // one (rtol, atol) row per trajectory, held in per-lane registers by the CYRK_TOL_PER_TRAJ build of the kernels;
+        // rtol is floored like the reference does in place (rk.cpp:600-608)
+        std::vector<double> rt(a.rtols, a.rtols + B * NY);
+        for (double& r : rt) if (r < 100.0 * std::numeric_limits<double>::epsilon()) r = 100.0 * std::numeric_limits<double>::epsilon();
+        if (h->d_rtol.ensure(B * NY * 8) || h->d_atol.ensure(B * NY * 8)) return -1;
+        CU_TRY(cudaMemcpyAsync(h->d_rtol.p, rt.data(), B * NY * 8, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(cudaMemcpyAsync(h->d_atol.p, a.atols, B * NY * 8, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));          // (`rt` is a temporary)
+        p.rtol_pt = h->d_rtol.as<double>(); p.atol_pt = h->d_atol.as<double>();
     }
     p.max_step = a.max_step;
     p.has_max_step = (a.max_step < std::numeric_limits<double>::infinity()) ? 1 : 0;
@@ -831,7 +859,9 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
                     }
             }
         }
-        if (!fwd0) std::reverse(te.begin(), te.end());
+        if (te_pt) te.assign(a.t_eval, a.t_eval + B * a.n_t_eval);
+        if (!fwd0) for (size_t r = 0; r < (te_pt ? B : 1); r++) std::reverse(te.begin() + r * a.n_t_eval, te.begin() + (r + 1) * a.n_t_eval);
+        p.t_eval_stride = te_pt ? (unsigned)a.n_t_eval : 0u;
         if (h->d_teval.ensure(te.size() * sizeof(double))) return -1;
         // synchronous on purpose: `te` is a stack-owned temporary
         CU_TRY(cudaMemcpyAsync(h->d_teval.p, te.data(), te.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -1213,6 +1243,8 @@ static int solve_thread_streamed(Handle* h, const SolveArgs& a, const Dispatch* 
             ac.t_span = h->d_tspan.as<double>() + (per_span ? 2 * off : 0);
             ac.n_t_span = per_span ? n : 1;
             ac.flags |= CYRK_FLAG_DEVICE_IO;
+            if (a.flags & CYRK_FLAG_TOL_PER_TRAJ) { ac.rtols = a.rtols + off * NY; ac.atols = a.atols + off * NY; ac.n_rtols = ac.n_atols = n * NY; }
+            if (a.n_t_eval && (a.flags & CYRK_FLAG_T_EVAL_PER_TRAJ)) ac.t_eval = a.t_eval + off * a.n_t_eval;
             s->force = Handle::Force();
             s->force.active = true;
             s->force.ev_base = ev_base;
@@ -1295,6 +1327,7 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     const bool device_io = (a.flags & CYRK_FLAG_DEVICE_IO) != 0;
     const bool want_rows = a.store_mode == CYRK_STORE_ROWS;
     if (a.num_extra != 0) { set_error("the CTA-per-trajectory path does not capture extra outputs yet"); return -1; }
+    if (a.flags & (CYRK_FLAG_T_EVAL_PER_TRAJ | CYRK_FLAG_TOL_PER_TRAJ)) { set_error("per-trajectory t_eval / tolerances are available on the thread-per-trajectory path (n_y <= 32) only"); return -1; }
     const bool dense = a.dense_output != 0;
     const bool user_rhs = a.rhs_id >= CYRK_RHS_USER_BASE;
     if (!user_rhs && (a.n_args == 0 || a.args_len < 8)) { set_error("largey problems need args = (decay_rate, ...)"); return -1; }
@@ -1526,7 +1559,12 @@ static int validate(const SolveArgs& a)
     }
     if (!a.y0 || a.n_y == 0) { set_error("y0 is required and n_y must be > 0"); return -1; }
     if (!a.t_span || !(a.n_t_span == 1 || a.n_t_span == a.n_traj)) { set_error("t_span must hold 1 or n_traj (t_start, t_end) pairs"); return -1; }
-    if (!a.rtols || !a.atols || a.n_rtols == 0 || a.n_atols == 0 || (a.n_rtols > 1 && a.n_rtols != a.n_y) ||
+    if (a.flags & CYRK_FLAG_TOL_PER_TRAJ) {
+        if (!a.rtols || !a.atols || a.n_rtols != a.n_traj * a.n_y || a.n_atols != a.n_traj * a.n_y) {
+            set_error("CYRK_FLAG_TOL_PER_TRAJ: rtols and atols must each hold n_traj * n_y entries");
+            return -1;
+        }
+    } else if (!a.rtols || !a.atols || a.n_rtols == 0 || a.n_atols == 0 || (a.n_rtols > 1 && a.n_rtols != a.n_y) ||
         (a.n_atols > 1 && a.n_atols != a.n_y)) {
         set_error("rtols/atols must have 1 or n_y entries (CyrkErrorCodes::BAD_CONFIG_DATA, -22)");
         return -1;
@@ -1558,11 +1596,15 @@ static int validate(const SolveArgs& a)
             }
         }
     }
-    for (size_t i = 0; i < a.n_t_eval; i++) {
-        if (!std::isfinite(a.t_eval[i])) { set_error("t_eval[%zu] = %g is not finite", i, a.t_eval[i]); return -1; }
-        if (i > 0 && !device_io && (fwd0 ? (a.t_eval[i] < a.t_eval[i - 1]) : (a.t_eval[i] > a.t_eval[i - 1]))) {
-            set_error("t_eval must be ordered in the direction of integration (t_eval[%zu] = %g follows %g)", i, a.t_eval[i], a.t_eval[i - 1]);
-            return -1;
+    const size_t n_te_rows = (a.flags & CYRK_FLAG_T_EVAL_PER_TRAJ) ? a.n_traj : 1;
+    for (size_t r = 0; r < n_te_rows; r++) {
+        const double* te = a.t_eval + r * a.n_t_eval;
+        for (size_t i = 0; i < a.n_t_eval; i++) {
+            if (!std::isfinite(te[i])) { set_error("t_eval[%zu] = %g is not finite", r * a.n_t_eval + i, te[i]); return -1; }
+            if (i > 0 && !device_io && (fwd0 ? (te[i] < te[i - 1]) : (te[i] > te[i - 1]))) {
+                set_error("t_eval must be ordered in the direction of integration (t_eval[%zu] = %g follows %g)", r * a.n_t_eval + i, te[i], te[i - 1]);
+                return -1;
+            }
         }
     }
     return 0;
@@ -1598,6 +1640,7 @@ static int solve_impl(Handle* h, const SolveArgs& a)
         h->solved = true;
         return 0;
     }
+    if ((a.flags & CYRK_FLAG_TOL_PER_TRAJ) && disp.use_feature("-DCYRK_TOL_PER_TRAJ=1")) return -1;
     const Dispatch* pe = &disp;
     if ((size_t)pe->ny != a.n_y) { set_error("right-hand side %d has n_y = %d but y0 has n_y = %zu", a.rhs_id, pe->ny, a.n_y); return -1; }
     if ((size_t)pe->nextra != a.num_extra) {
@@ -1794,6 +1837,26 @@ int cyrk_b200_rhs_compile(const char* source, const char* entry, size_t n_y, siz
 {
     return user_rhs_register(source, entry, n_y, n_extra, args_bytes, n_event_funcs, log, log_len);
 }
+
+int cyrk_b200_jit_compile(int rhs_id, int method, int variant, unsigned flags)
+{
+    // Compile-only: warms the process and disk caches for a run-time compiled kernel (user right-hand side, or the
+    // per-trajectory-tolerance build of a built-in problem).  Needs NVRTC, not a GPU.
+    registry_init();
+    if (method < CYRK_METHOD_RK23 || method > CYRK_METHOD_DOP853 || variant < 0 || variant >= VAR_COUNT) { set_error("bad method / variant"); return -1; }
+    const bool strict = (flags & CYRK_FLAG_STRICT_FP) != 0;
+    const char* defs = (flags & CYRK_FLAG_TOL_PER_TRAJ) ? "-DCYRK_TOL_PER_TRAJ=1" : "";
+    int id = rhs_id;
+    if (rhs_id < CYRK_RHS_USER_BASE) {
+        const ProblemEntry* pe = registry_lookup(strict ? FP_STRICT : FP_FAST, rhs_id);
+        if (!pe) { set_error("right-hand side %d has no thread-per-trajectory kernels", rhs_id); return -1; }
+        id = builtin_jit_id(pe->struct_name, pe->ny, pe->nextra, pe->nargs_dbl);
+    }
+    g_last_error.clear();
+    return jit_compile_only(id, "solve", method, variant, strict, defs);
+}
+
+void cyrk_b200_jit_cache_stats(unsigned long long* compiled, unsigned long long* disk_hits) { jit_cache_stats(compiled, disk_hits); }
 
 void* cyrk_b200_result_create(void) { return new Handle(); }
 

@@ -73,6 +73,8 @@ struct BatchParams {
     unsigned      t_span_stride; // 0 = shared, 2 = per trajectory
     double rtol[CYRK_MAX_NY];    // already floored at 100*eps on the host (rk.cpp:600-608)
     double atol[CYRK_MAX_NY];
+    const double* rtol_pt;       // CYRK_TOL_PER_TRAJ kernels: [n_traj][NY] (floored like rtol[]); NULL otherwise
+    const double* atol_pt;       //                            [n_traj][NY]
     double max_step;             // INF = none
     int    has_max_step;         // max_step < INF (lets the kernel test it with a uniform integer compare)
     double first_step;           // 0 = automatic
@@ -81,6 +83,7 @@ struct BatchParams {
     // ---- t_eval (shared by the batch; ascending; for backward runs the host passes the reversed copy)
     const double* t_eval;
     unsigned      n_t_eval;
+    unsigned      t_eval_stride; // 0 = shared; n_t_eval = one row per trajectory (CYRK_FLAG_T_EVAL_PER_TRAJ)
     // ---- per-trajectory results
     int*      status;            // [n_traj]
     unsigned* size;              // rows the reference would have saved

@@ -76,6 +76,7 @@ void CYRK_CAT(cyrk_register, CYRK_INST_PROB, CYRK_FP_NS)()
 {
     ProblemEntry* e = registry_slot(CYRK_FP_MODE, CYRK_INST_ID);
     e->present = true;
+    e->struct_name = CYRK_STR(CYRK_INST_PROB);
     e->ny = CYRK_INST_PROB::NY;
     e->nextra = CYRK_INST_PROB::NEXTRA;
     e->nargs_dbl = CYRK_INST_PROB::NARGS_DBL;

@@ -18,6 +18,7 @@ struct KernelEntry {
 struct ProblemEntry {
     bool present;
     int ny, nextra, nargs_dbl;
+    const char* struct_name;             // the problem's struct in problems_builtin.cuh (feature builds are compiled on demand)
     KernelEntry solve[3][VAR_COUNT];     // [method - 3][variant]
     cudaError_t (*dense_eval[3])(const DenseEvalParams&, int grid, int block, cudaStream_t);
     cudaError_t (*prep[3])(const BatchParams&, double* prep, int grid, int block, cudaStream_t);

@@ -35,7 +35,7 @@ EVENT_IDS = dict(y0_gt_50=0, y1_lt_50=1, t_gt_5=2, lorenz_t_ge_5=3, lorenz_y_ran
                  y0=6, y1=7, t_minus_arg4=8, abs_y0_minus_arg4=9)
 
 STORE_FINAL, STORE_ROWS = 0, 1
-FLAG_STRICT_FP, FLAG_DEVICE_IO = 1, 2
+FLAG_STRICT_FP, FLAG_DEVICE_IO, FLAG_T_EVAL_PER_TRAJ, FLAG_TOL_PER_TRAJ = 1, 2, 4, 8
 
 
 def find_ode_method_int(method: str) -> int:
@@ -413,7 +413,8 @@ def cysolve_ivp_batch(
     Same names/defaults as ``pysolve_ivp`` (pysolver.pyx:348-368) plus:
       y0        (B, n_y); args (n_args,) shared or (B, n_args) per trajectory (float64, the
                 reference's ``double[::1] args`` convention) or ``bytes`` for an opaque struct blob;
-                t_span (2,) shared or (B, 2).
+                t_span (2,) shared or (B, 2); t_eval (n,) shared or (B, n) per trajectory;
+                rtol / atol scalar, (n_y,) per component, or (B, n_y) / (B, 1) per trajectory.
       store     'rows'  -> every row the reference would save (``result[i].t/.y``)
                 'final' -> only the last row and the counters (``result.y_last``)
       strict_fp run the -fmad=false kernels (the reference's rounding: no FMA contraction)
@@ -491,8 +492,19 @@ def cysolve_ivp_batch(
         a_buf = a
     rt = np.atleast_1d(np.asarray(rtol, dtype=np.float64)).copy()
     at = np.atleast_1d(np.asarray(atol, dtype=np.float64)).copy()
+    tol_per_traj = rt.ndim == 2 or at.ndim == 2
+    if tol_per_traj:
+        # one tolerance row per trajectory: (B, n_y), or (B, 1) broadcast over the components
+        try:
+            rt = np.ascontiguousarray(np.broadcast_to(rt if rt.ndim == 2 else rt[None, :], (B, ny)))
+            at = np.ascontiguousarray(np.broadcast_to(at if at.ndim == 2 else at[None, :], (B, ny)))
+        except ValueError:
+            raise ValueError("per-trajectory rtol / atol must have shape (B, n_y) or (B, 1)") from None
     te = None if t_eval is None else np.ascontiguousarray(t_eval, dtype=np.float64)
-    n_te = 0 if te is None else te.size
+    t_eval_per_traj = te is not None and te.ndim == 2
+    if t_eval_per_traj and te.shape[0] != B:
+        raise ValueError("per-trajectory t_eval must have shape (B, n_t_eval)")
+    n_te = 0 if te is None else (te.shape[1] if t_eval_per_traj else te.size)
 
     events = list(events) if events else []
     ev_ids = np.zeros(max(len(events), 1), dtype=np.int32)
@@ -506,7 +518,8 @@ def cysolve_ivp_batch(
         ev_max[i] = SIZE_MAX if ev.max_allowed is None else int(ev.max_allowed)
 
     store_mode = {"final": STORE_FINAL, "rows": STORE_ROWS, "steps": STORE_ROWS, "t_eval": STORE_ROWS}[store]
-    flags = (FLAG_STRICT_FP if strict_fp else 0) | (FLAG_DEVICE_IO if device_io else 0)
+    flags = ((FLAG_STRICT_FP if strict_fp else 0) | (FLAG_DEVICE_IO if device_io else 0) |
+             (FLAG_T_EVAL_PER_TRAJ if t_eval_per_traj else 0) | (FLAG_TOL_PER_TRAJ if tol_per_traj else 0))
     call_args = (
         rid, method_int, B,
         ts.ctypes.data, n_t_span,

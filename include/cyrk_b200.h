@@ -77,6 +77,9 @@ extern "C" {
 /* Flags. */
 #define CYRK_FLAG_STRICT_FP   1u  /* kernels compiled with -fmad=false: reference's rounding (no FMA) */
 #define CYRK_FLAG_DEVICE_IO   2u  /* y0/args/t_span are DEVICE pointers; results stay on the device   */
+#define CYRK_FLAG_T_EVAL_PER_TRAJ 4u /* t_eval holds n_traj rows of n_t_eval sample times (one row per trajectory) */
+#define CYRK_FLAG_TOL_PER_TRAJ    8u /* rtols / atols hold n_traj rows of n_y entries (n_rtols == n_atols == n_traj * n_y);
+                                        thread-per-trajectory path; the kernels of this option are compiled on first use */
 
 #define CYRK_EVENT_NO_LIMIT ((size_t)-1)   /* Event::max_allowed default, c_events.hpp:33 */
 
@@ -104,9 +107,17 @@ int cyrk_b200_rhs_info(int rhs_id, size_t* n_y, size_t* n_extra, size_t* args_by
  *     __device__ double <entry>(unsigned i, double t, const double* y, unsigned n, const char* args);      -> dy_i
  *     __device__ double <entry>_event(int id, double t, const double* y, unsigned n, const char* args);     -> g_id
  * Returns an id >= CYRK_RHS_USER_BASE, or -1
- * (compile log in `log`).  Compiled modules are cached by source hash for the process lifetime. */
+ * (compile log in `log`).  Compiled modules are cached by source hash per process and on disk (see below). */
 int cyrk_b200_rhs_compile(const char* source, const char* entry, size_t n_y, size_t n_extra,
                           size_t args_bytes, size_t n_event_funcs, char* log, size_t log_len);
+/* Run-time compiled kernels (user right-hand sides; feature builds of the built-ins such as CYRK_FLAG_TOL_PER_TRAJ) are
+ * cached per process AND on disk: $CYRK_B200_CACHE_DIR, else $XDG_CACHE_HOME/cyrk_b200, else ~/.cache/cyrk_b200
+ * (CYRK_B200_CACHE=0 disables); the key hashes the complete source, every embedded solver header, the options and the NVRTC
+ * version.  cyrk_b200_jit_compile compiles one solve kernel ahead of time (variant: 0 final state, 1 rows / t_eval / dense,
+ * 2 + events, 4 events with final state only; flags: CYRK_FLAG_STRICT_FP / CYRK_FLAG_TOL_PER_TRAJ) -- it needs NVRTC but
+ * no GPU, so a build box can warm the cache.  Returns 0 / -1.  jit_cache_stats: kernels compiled / found on disk so far. */
+int  cyrk_b200_jit_compile(int rhs_id, int method, int variant, unsigned flags);
+void cyrk_b200_jit_cache_stats(unsigned long long* compiled, unsigned long long* disk_hits);
 
 /* ---- solve --------------------------------------------------------------------------------- */
 /* Arguments mirror numba_cysolve_ivp (numba_c_api_.cpp:10-30), batched:
@@ -119,9 +130,10 @@ int cyrk_b200_rhs_compile(const char* source, const char* entry, size_t n_y, siz
  *                             == n_traj per trajectory
  *   max_num_steps, max_ram_MB as the reference (cy/c_common.cpp:20-56); 0 / 2000 are its defaults
  *   dense_output              keep every step's interpolant on the device for call_vectorize
- *   t_eval, n_t_eval          shared sample times (ordered in the direction of integration)
+ *   t_eval, n_t_eval          sample times (ordered in the direction of integration), always a HOST pointer: n_t_eval shared
+ *                             values, or with CYRK_FLAG_T_EVAL_PER_TRAJ [n_traj][n_t_eval]
  *   event_ids/dirs/max        n_events entries; max == CYRK_EVENT_NO_LIMIT never terminates
- *   rtols/atols               1 or n_y entries
+ *   rtols/atols               1 or n_y entries (HOST pointers), or with CYRK_FLAG_TOL_PER_TRAJ [n_traj][n_y] each
  *   max_step, first_step      INFINITY / 0.0 are the reference defaults
  *   expected_size             rows (and interpolants) reserved per trajectory in CYRK_STORE_ROWS /
  *                             dense mode; 0 = automatic.  If a trajectory needs more, the batch is

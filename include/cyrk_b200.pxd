@@ -85,6 +85,8 @@ cdef extern from "cyrk_b200.h" nogil:
     size_t cyrk_b200_get_h2d_bytes(void* h)
     size_t cyrk_b200_get_d2h_bytes(void* h)
     size_t cyrk_b200_get_lazy_d2h_bytes(void* h)
+    int cyrk_b200_jit_compile(int rhs_id, int method, int variant, unsigned flags)
+    void cyrk_b200_jit_cache_stats(unsigned long long* compiled, unsigned long long* disk_hits)
     int cyrk_b200_set_option(const char* name, int value)
     double cyrk_b200_measure_fp64_tflops(int device)
     int cyrk_b200_debug_sincos(const double* x, double* sin_out, double* cos_out, size_t n, int device)

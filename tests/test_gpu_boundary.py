@@ -1,0 +1,139 @@
+"""GPU: the rest of the drop-in boundary of SURVEY.md 8(b) row 1 -- t_eval and tolerances may be shared or PER
+TRAJECTORY (a loop of reference calls can pass different ones to every cysolve_ivp call,
+CyRK/cy/cysolver_api.pyx:416-469: `t_eval`, `rtols_vec`, `atols_vec`).  Every trajectory is checked against its own
+oracle solve."""
+import numpy as np
+import pytest
+
+import cyrk_b200 as c
+
+pytestmark = pytest.mark.gpu
+LV = [1.5, 1.0, 3.0, 1.0]
+
+
+def _opt(name, value):
+    assert c.lib().cyrk_b200_set_option(name.encode(), int(value)) == 0
+
+
+def _lv_batch(B, seed):
+    rng = np.random.default_rng(seed)
+    y0 = np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)
+    rt = 10.0 ** rng.uniform(-9, -5, (B, 2))
+    at = rt * 10.0 ** rng.uniform(-3, -1, (B, 2))
+    return y0, rt, at
+
+
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fma"])
+@pytest.mark.parametrize("method", ["RK23", "RK45", "DOP853"])
+def test_per_trajectory_tolerances_match_one_oracle_solve_each(oracle, method, strict):
+    B = 96
+    y0, rt, at = _lv_batch(B, 31)
+    if method == "RK23":
+        rt, at = rt * 100, at * 100
+    r = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, method=method, args=LV, rtol=rt, atol=at, store="rows",
+                            expected_size=4096, strict_fp=strict)
+    assert (r.status == 1).all()
+    same = 0
+    for i in range(B):
+        ref = oracle.solve("lotkavolterra", (0.0, 10.0), y0[i], method, rt[i], at[i], args=LV)
+        v = r[i]
+        ok = v.size == ref.size and v.steps_taken == ref.steps_taken and int(r.nfev[i]) == ref.nfev
+        same += ok
+        assert np.all(np.abs(v.y[:, -1] - ref.y[:, -1]) <= 10 * rt[i] * np.abs(ref.y[:, -1]) + 10 * at[i]), i
+        if ok:
+            assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
+    assert same == B if strict else same >= B - 1
+    # a shared tolerance row passed per trajectory is the shared-tolerance solve, bit for bit (same operations)
+    r1 = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, method=method, args=LV, rtol=[1e-7, 1e-6], atol=[1e-9, 1e-8],
+                             store="final", strict_fp=True)
+    r2 = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, method=method, args=LV, rtol=np.tile([1e-7, 1e-6], (B, 1)),
+                             atol=np.tile([1e-9, 1e-8], (B, 1)), store="final", strict_fp=True)
+    for name in ("status", "steps_taken", "n_rejected", "nfev", "y_last"):
+        assert np.array_equal(getattr(r1, name), getattr(r2, name)), name
+
+
+def test_per_trajectory_tolerances_through_the_pipelined_and_streamed_paths():
+    """The chunked final-state pipeline and the streamed rows path must hand every chunk ITS tolerance rows."""
+    B = 6000
+    y0, rt, at = _lv_batch(B, 32)
+    kw = dict(method="RK45", args=LV, rtol=rt, atol=at)
+    try:
+        _opt("pipe_min", 0); _opt("stream", 0)
+        a_final = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, store="final", **kw)
+        a_rows = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, store="rows", expected_size=512, **kw)
+        _opt("pipe_min", 1024); _opt("pipe_chunk", 1024)
+        b_final = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, store="final", **kw)
+        assert b_final.launches >= 4
+        _opt("stream", 1); _opt("stream_chunk", 1024)
+        b_rows = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, store="rows", expected_size=512, **kw)
+        assert b_rows.launches > a_rows.launches
+    finally:
+        _opt("pipe_min", 1 << 18); _opt("pipe_chunk", 1 << 20); _opt("stream", 1); _opt("stream_chunk", 0)
+    for a, b in ((a_final, b_final), (a_rows, b_rows)):
+        for name in ("status", "size", "steps_taken", "n_rejected", "nfev", "t_last", "y_last"):
+            assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    # looser tolerances -> fewer steps: the rows really were used per trajectory
+    loose = rt[:, 0] > 1e-6
+    assert a_final.steps_taken[loose].mean() < a_final.steps_taken[~loose].mean()
+
+
+@pytest.mark.parametrize("backward", [False, True], ids=["fwd", "bwd"])
+def test_per_trajectory_t_eval_matches_one_oracle_solve_each(oracle, backward):
+    B = 80
+    rng = np.random.default_rng(33)
+    y0 = np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)
+    span = (10.0, 0.0) if backward else (0.0, 10.0)
+    n = 37
+    # every trajectory samples its own times: a random sub-interval, plus samples outside the span for some
+    lo = rng.uniform(-0.5, 3.0, B); hi = rng.uniform(6.0, 10.0, B)
+    te = lo[:, None] + (hi - lo)[:, None] * np.sort(rng.uniform(0, 1, (B, n)), axis=1)
+    te[:, -1] = np.where(np.arange(B) % 3 == 0, 10.0, te[:, -1])
+    if backward:
+        te = te[:, ::-1].copy()
+    for dense in (False, True):
+        r = c.cysolve_ivp_batch("lotkavolterra", span, y0, method="RK45", args=LV, rtol=1e-7, atol=1e-9, t_eval=te,
+                                dense_output=dense, strict_fp=True)
+        assert r.row_capacity == n
+        for i in range(B):
+            ref = oracle.solve("lotkavolterra", span, y0[i], "RK45", 1e-7, 1e-9, args=LV, t_eval=te[i], dense_output=dense)
+            v = r[i]
+            assert v.status == ref.status and v.size == ref.size and v.steps_taken == ref.steps_taken, i
+            assert np.array_equal(v.t, ref.t)
+            assert np.all(np.abs(v.y - ref.y) <= 10 * 1e-7 * np.abs(ref.y) + 10 * 1e-9)
+    with pytest.raises(c.CyrkB200Error, match="ordered in the direction"):
+        bad = te.copy(); bad[5, 3], bad[5, 4] = bad[5, 4], bad[5, 3] + (1 if backward else -1)
+        c.cysolve_ivp_batch("lotkavolterra", span, y0, method="RK45", args=LV, t_eval=bad)
+
+
+def test_per_trajectory_t_eval_streamed_equals_single_arena():
+    B = 3000
+    rng = np.random.default_rng(34)
+    y0 = np.stack([rng.uniform(5, 15, B), rng.uniform(2.5, 7.5, B)], 1)
+    te = np.sort(rng.uniform(0.0, 10.0, (B, 50)), axis=1)
+    kw = dict(method="RK45", args=LV, rtol=1e-7, atol=1e-9, t_eval=te)
+    try:
+        _opt("stream", 0)
+        a = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, **kw)
+        _opt("stream", 1); _opt("stream_chunk", 700)
+        b = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, **kw)
+    finally:
+        _opt("stream", 1); _opt("stream_chunk", 0)
+    assert b.launches > a.launches
+    for name in ("status", "size", "steps_taken", "nfev", "t_last", "y_last", "t_rows", "y_rows"):
+        assert np.array_equal(getattr(a, name), getattr(b, name), equal_nan=True), name
+
+
+def test_per_trajectory_tolerances_with_a_user_right_hand_side(oracle):
+    src = """
+    __device__ void lv_user(double* dy, double t, const double* y, const char* args) {
+        const double* a = (const double*)args;
+        dy[0] = a[0] * y[0] - a[1] * y[0] * y[1];
+        dy[1] = -a[2] * y[1] + a[3] * y[0] * y[1];
+    }"""
+    u = c.UserRHS(src, "lv_user", n_y=2, args_bytes=32)
+    B = 40
+    y0, rt, at = _lv_batch(B, 35)
+    r = c.cysolve_ivp_batch(u, (0.0, 10.0), y0, method="RK45", args=LV, rtol=rt, atol=at, store="final", strict_fp=True)
+    ob = [oracle.solve("lotkavolterra", (0.0, 10.0), y0[i], "RK45", rt[i], at[i], args=LV) for i in range(B)]
+    assert np.array_equal(r.steps_taken, [o.steps_taken for o in ob])
+    assert np.array_equal(r.status, [o.status for o in ob])
