@@ -99,6 +99,7 @@ static int g_opt_two_pass = 1;        // t_eval / dense_output without events or
 static int g_opt_dense_store = 0;     // two-pass path with dense_output: 0 = the 40-byte step records are the dense store (sol(t)
                                       // recomputes the step it needs), 1 = materialise every [y_old | Q] interpolant as well
 static int g_opt_events_variant = 1;  // events with store='final' and no t_eval / dense store: the VAR_EVENTS kernels (0 = VAR_FULL)
+static int g_opt_events_two_pass = 1; // ... as detection solve + one thread per triggered step (event_roots_kernel); 0 = one-pass VAR_EVENTS
 static int g_opt_root_batch = 12;     // measured: 8..16 is the flat optimum on the C3 workload (profiles/r01_notes.md)
 static int g_opt_ctas_per_sm = 0;
 
@@ -175,6 +176,8 @@ struct Handle {
     DevBuf d_q_t, d_q_out, d_q_code, d_scratch, d_prep, d_rtol, d_atol;
     DevBuf d_st;                            // step records of the two-pass t_eval / dense path
     DevBuf d_ev_t2, d_ev_y2, d_ev_off, d_scan;   // packed (CSR) event lists: hits back to back + offsets
+    DevBuf d_evq, d_evq_count;              // work items of the two-pass events path
+    size_t evq_seen = 0;                    // items the last two-pass events solve pushed (sizes the next queue of a reused handle)
     PinBuf h_ev_off;
     bool ev_packed = false;                 // host mirrors of the event lists are CSR-packed (host-buffer solves on the thread path)
     size_t ev_total = 0;                    // hits in the packed arrays
@@ -236,7 +239,7 @@ struct Handle {
         DevBuf* dbs[] = {&d_y0, &d_args, &d_tspan, &d_teval, &d_queue, &d_status, &d_size, &d_steps, &d_nrej, &d_nfev,
                          &d_tlast, &d_ylast, &d_trows, &d_yrows, &d_dense_t, &d_dense_state, &d_dense_count, &d_ev_t,
                          &d_ev_y, &d_ev_count, &d_ev_term, &d_q_t, &d_q_out, &d_q_code, &d_scratch, &d_prep, &d_rtol, &d_atol,
-                         &d_st, &d_ev_t2, &d_ev_y2, &d_ev_off, &d_scan};
+                         &d_st, &d_ev_t2, &d_ev_y2, &d_ev_off, &d_scan, &d_evq, &d_evq_count};
         for (DevBuf* b : dbs) b->release();
         PinBuf* pbs[] = {&h_status, &h_size, &h_steps, &h_nrej, &h_nfev, &h_tlast, &h_ylast, &h_trows, &h_yrows,
                          &h_dense_count, &h_ev_t, &h_ev_y, &h_ev_count, &h_ev_term, &h_stage, &h_ev_off};
@@ -336,6 +339,11 @@ struct Dispatch {
             if (jit_id < 0) { set_error("cannot register built-in problem %s for run-time compilation", pe->struct_name); return -1; }
         }
         return 0;
+    }
+    cudaError_t event_roots(int method, const BatchParams& p, int grid, int block, cudaStream_t s) const
+    {
+        if (pe && jit_defs.empty()) return pe->event_roots[method - 3](p, grid, block, s);
+        return user_rhs_launch_event_roots(pe ? jit_id : rhs_id, method, strict, device, p, grid, block, s, jit_defs.c_str());
     }
     cudaError_t step_dense(int method, const StepDenseParams& p, int grid, int block, cudaStream_t s) const
     {
@@ -791,7 +799,9 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         if (getenv("CYRK_B200_DEBUG")) fprintf(stderr, "[cyrk_b200] %s: block %d, %d CTAs/SM, grid %d\n", pe->name(a.method, solve_variant), block, ctas, grid);
         return 0;
     };
-    if (pick_grid(two_pass ? VAR_STEPS : variant)) return -1;
+    // Events with store='final': detection solve + one thread per triggered step (rk_core.cuh, event_roots_body)
+    bool ev2 = variant == VAR_EVENTS && g_opt_events_two_pass != 0;
+    if (pick_grid(two_pass ? VAR_STEPS : (ev2 ? VAR_EVDETECT : variant))) return -1;
 
     // ---- host buffers + final-state variant + a batch worth cutting up: pipelined copy/compute path
     if (!device_io && (variant == VAR_LEAN || variant == VAR_LEAN_SHARED) && g_opt_pipe_min > 0 && B >= (size_t)g_opt_pipe_min)
@@ -989,8 +999,11 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
         CU_TRY(cudaStreamSynchronize(h->stream));
         { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; if (getenv("CYRK_B200_DEBUG")) fprintf(stderr, "[cyrk_b200] step_dense (+ last row): %.3f ms, %u threads per trajectory\n", ms, q.step_threads); }
-    } else
+    } else {
+    size_t evq_cap = std::max<size_t>(B * 16, h->evq_seen + h->evq_seen / 8);
+    int guard = 0;
     for (int pass = 0; pass < 2; pass++) {
+        if (++guard > 8) { set_error("internal: the events solve did not settle"); return -1; }
         if (want_rows) {
             if (h->d_trows.ensure(B * row_cap * 8) || h->d_yrows.ensure(B * row_cap * NDY * 8)) return -1;
             p.t_rows = h->d_trows.as<double>();
@@ -1025,8 +1038,32 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             h->launches++;
             p.prep = h->d_prep.as<double>();
         }
-        if (pe->launch(a.method, variant, p, grid, block, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("solve kernel launch failed"); return -1; }
+        if (ev2) {
+            if (h->d_evq.ensure(evq_cap * CYRK_EVQ_ITEM_DOUBLES(NY) * 8) || h->d_evq_count.ensure(16)) return -1;
+            CU_TRY(cudaMemsetAsync(h->d_evq_count.p, 0, 16, h->stream));
+            p.evq_items = h->d_evq.as<double>(); p.evq_count = h->d_evq_count.as<unsigned long long>(); p.evq_cap = evq_cap;
+        }
+        if (pe->launch(a.method, ev2 ? VAR_EVDETECT : variant, p, grid, block, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("solve kernel launch failed"); return -1; }
         h->launches++;
+        if (ev2) {
+            // the number of parked steps sizes the second half; more than the queue holds -> deterministic re-run
+            unsigned long long cnt[2] = {0, 0};
+            CU_TRY(cudaMemcpyAsync(cnt, h->d_evq_count.p, 16, cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            if (getenv("CYRK_B200_DEBUG")) fprintf(stderr, "[cyrk_b200] event detection: %llu triggered steps (queue %zu), fallback flag %llu\n", cnt[0], evq_cap, cnt[1]);
+            if (cnt[1] != 0) {             // a triggered step that was booked without stages: only the one-pass kernel reproduces it
+                ev2 = false;
+                if (pick_grid(variant)) return -1;
+                pass--; continue;
+            }
+            if (cnt[0] > evq_cap) { evq_cap = (size_t)cnt[0]; pass--; continue; }
+            h->evq_seen = (size_t)cnt[0];
+            if (cnt[0] > 0) {
+                const int rgrid = (int)std::min<unsigned long long>((cnt[0] + 127) / 128, (unsigned long long)device_sm_count(h->device) * 32);
+                if (pe->event_roots(a.method, p, rgrid, 128, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("event_roots kernel launch failed"); return -1; }
+                h->launches++;
+            }
+        }
         CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
 
         // counters come back first: they decide whether any arena overflowed
@@ -1035,7 +1072,14 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
         if (a.n_events && download(h, h->h_ev_count, h->d_ev_count, B * a.n_events * 4)) return -1;
         if (!need_check) break;
+        unsigned long long evq_flag = 0;
+        if (ev2) CU_TRY(cudaMemcpyAsync(&evq_flag, h->d_evq_count.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
+        if (ev2 && evq_flag != 0) {        // a Brent search failed (-30 / -31): the one-pass kernel reproduces what the reference does next
+            ev2 = false; h->kernel_ms = 0.f;
+            if (pick_grid(variant)) return -1;
+            pass--; continue;
+        }
         {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1);
@@ -1054,6 +1098,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         row_cap = std::max(row_cap, (force.active && !force.row_cap && mx_rows > row_cap) ? mx_rows + mx_rows / 16 + 8 : mx_rows);
         dense_cap = std::max(dense_cap, mx_dense);
         ev_cap = std::max(ev_cap, mx_ev);
+    }
     }
     h->ev_packed = false; h->ev_total = 0;
     if (a.n_events && (!device_io || force.active)) {
@@ -2102,6 +2147,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "stream_chunk")) { g_opt_stream_chunk = value; return 0; }
     if (!strcmp(name, "shared_args")) { g_opt_shared_args = value; return 0; }
     if (!strcmp(name, "events_variant")) { g_opt_events_variant = value; return 0; }
+    if (!strcmp(name, "events_two_pass")) { g_opt_events_two_pass = value; return 0; }
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
     if (!strcmp(name, "cta_kernel")) { g_opt_cta_kernel = value; return 0; }

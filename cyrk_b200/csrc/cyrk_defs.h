@@ -49,8 +49,15 @@ enum Variant : int {
                     // the same decisions from ~25 % less code -- the events kernels are instruction-fetch bound
     VAR_LEAN_SHARED = 5, // VAR_LEAN for a batch whose args are shared: the right-hand side reads them from the kernel
                     // parameter block (constant bank / uniform registers) instead of per-lane registers
-    VAR_COUNT = 6
+    VAR_EVDETECT = 6, // events with store='final', first half of the two-pass events path: VAR_LEAN + per booked step the event
+                    // functions and the trigger test; a step that triggers is pushed as a work item (t_old, t_now, step, y_old,
+                    // hit slots) for event_roots_kernel, which redoes the step, builds its interpolant and runs the Brent
+                    // searches -- one thread per triggered step instead of one lane of a stepping warp
+    VAR_COUNT = 7
 };
+// one work item of the two-pass events path, in doubles: trajectory index, t_old, t_now, signed step, flags
+// (bit 31: the step terminates the trajectory; low bits: mask of triggered events), y_old[NY], hit slot of every event (uint32 pairs)
+#define CYRK_EVQ_ITEM_DOUBLES(ny) (5 + (ny) + CYRK_MAX_EVENTS / 2)
 #define CYRK_SHARED_ARGS_MAX 8     // doubles
 
 #define CYRK_MAX_NY 32        // thread-per-trajectory kernels: compile-time n_y up to this
@@ -113,6 +120,11 @@ struct BatchParams {
     unsigned* ev_count;          // [n_traj][n_events]
     int*      ev_term_index;     // [n_traj]   (-1 = none)
     unsigned  ev_cap;
+    // ---- two-pass events (VAR_EVDETECT + event_roots_kernel)
+    double*   evq_items;         // [evq_cap][CYRK_EVQ_ITEM_DOUBLES(NY)]
+    unsigned long long* evq_count;   // [0] items pushed (may exceed evq_cap: the host re-runs with that capacity);
+                                 // [1] != 0: a case only the one-pass kernel reproduces occurred (the host falls back to it)
+    unsigned long long evq_cap;
     // ---- scheduling
     const double* prep;          // [n_traj][NDY+2] start-up state from rk_prep_kernel, or NULL (set up inline)
     unsigned long long* queue;   // global work counter (zeroed before launch)

@@ -56,6 +56,12 @@ cudaError_t step_dense(const StepDenseParams& p, int grid, int block, cudaStream
     return cudaGetLastError();
 }
 template <int METHOD>
+cudaError_t event_roots(const BatchParams& p, int grid, int block, cudaStream_t s)
+{
+    event_roots_kernel<CYRK_INST_PROB, METHOD><<<grid, block, 0, s>>>(p);
+    return cudaGetLastError();
+}
+template <int METHOD>
 void fill(ProblemEntry* e)
 {
     e->solve[METHOD - 3][VAR_LEAN] = {launch<METHOD, VAR_LEAN>, occupancy<METHOD, VAR_LEAN>, CYRK_STR(CYRK_INST_PROB) "/lean"};
@@ -64,6 +70,8 @@ void fill(ProblemEntry* e)
     e->solve[METHOD - 3][VAR_FULL] = {launch<METHOD, VAR_FULL>, occupancy<METHOD, VAR_FULL>, CYRK_STR(CYRK_INST_PROB) "/full"};
     e->solve[METHOD - 3][VAR_STEPS] = {launch<METHOD, VAR_STEPS>, occupancy<METHOD, VAR_STEPS>, CYRK_STR(CYRK_INST_PROB) "/steps"};
     e->solve[METHOD - 3][VAR_EVENTS] = {launch<METHOD, VAR_EVENTS>, occupancy<METHOD, VAR_EVENTS>, CYRK_STR(CYRK_INST_PROB) "/events"};
+    e->solve[METHOD - 3][VAR_EVDETECT] = {launch<METHOD, VAR_EVDETECT>, occupancy<METHOD, VAR_EVDETECT>, CYRK_STR(CYRK_INST_PROB) "/event-detect"};
+    e->event_roots[METHOD - 3] = event_roots<METHOD>;
     e->dense_eval[METHOD - 3] = dense_eval<METHOD>;
     e->step_dense[METHOD - 3] = step_dense<METHOD>;
     e->prep[METHOD - 3] = prep<METHOD>;

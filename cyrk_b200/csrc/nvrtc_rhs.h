@@ -27,6 +27,8 @@ void jit_cache_stats(unsigned long long* compiled, unsigned long long* disk_hits
 int jit_compile_only(int rhs_id, const char* kind, int method, int variant, bool strict, const char* defs);
 cudaError_t user_rhs_launch_dense(int rhs_id, int method, bool strict, int device, const DenseEvalParams& p, int grid, int block,
                                   cudaStream_t s);
+cudaError_t user_rhs_launch_event_roots(int rhs_id, int method, bool strict, int device, const BatchParams& p, int grid, int block,
+                                        cudaStream_t s, const char* defs = "");
 cudaError_t user_rhs_launch_step_dense(int rhs_id, int method, bool strict, int device, const StepDenseParams& p, int grid, int block,
                                        cudaStream_t s);
 // Large systems (registered with n_y == 0): the source defines

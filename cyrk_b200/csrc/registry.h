@@ -23,6 +23,7 @@ struct ProblemEntry {
     cudaError_t (*dense_eval[3])(const DenseEvalParams&, int grid, int block, cudaStream_t);
     cudaError_t (*prep[3])(const BatchParams&, double* prep, int grid, int block, cudaStream_t);
     cudaError_t (*step_dense[3])(const StepDenseParams&, int grid, int block, cudaStream_t);
+    cudaError_t (*event_roots[3])(const BatchParams&, int grid, int block, cudaStream_t);
 };
 
 // table[fp_mode][rhs_id]

@@ -267,7 +267,8 @@ size_t   cyrk_b200_get_lazy_d2h_bytes(void* h); /* copied afterwards by getters 
  * "pipe_taper" (short first/last chunks, 0/1), "pipe_min" (smallest host-buffer final-state batch that takes the pipelined path;
  * default 256 Ki, 0 = never), "two_pass" (dense_output / t_eval without events or extras: 1 = step-parallel
  * interpolants when dense_output is set [default], 2 = also for t_eval alone, 0 = always the per-trajectory kernel; the
- * results are bitwise identical either way), "dense_store" (step-parallel path with dense_output: 0 [default] = the step records
+ * results are bitwise identical either way), "events_two_pass" (events with store='final': 1 [default] = detection solve + one thread per triggered step, 0 = roots found by
+ * the stepping lanes; same results), "dense_store" (step-parallel path with dense_output: 0 [default] = the step records
  * are the dense store and sol(t) recomputes the step it needs, 1 = every interpolant is materialised as well), "shared_args" (final-state solves whose args are shared read them from the
  * kernel parameter block instead of per-lane registers: 1 [default] / 0; bitwise identical with strict FP, within FMA-contraction
  * noise in the production build). */
