@@ -1,9 +1,9 @@
 #!/bin/bash
-P=${1:-r02_s3}
+P=${1:-r02_s4}
 O=gpurun_out
 mkdir -p $O
-timeout 1800 python -m pytest tests -m gpu -x -q > $O/${P}_gpu_tests.log 2>&1
-tail -3 $O/${P}_gpu_tests.log
-timeout 900 python scripts/bench_medium_ny.py > $O/${P}_medium_ny.log 2>&1
-tail -13 $O/${P}_medium_ny.log
+timeout 1800 python -m pytest tests -m gpu -q > $O/${P}_gpu_tests.log 2>&1
+tail -15 $O/${P}_gpu_tests.log
+for v in 0 1; do CYRK_EV2=$v timeout 600 python scripts/quick_c3full.py >> $O/${P}_c3full.log 2>&1; done
+cat $O/${P}_c3full.log
 echo done

@@ -43,8 +43,10 @@ def test_spring_chain_matches_oracle(oracle, ny, method, strict):
         assert np.all(np.abs(r_fin.y_last[i] - ref.y[:, -1]) <= tol(ref.y[:, -1]))
         assert int(r_fin.steps_taken[i]) == int(r_rows.steps_taken[i])
         if ok:
+            # raw step rows sit at slightly different times in two implementations (the error estimate is a difference of
+            # O(1) stage sums that cancels to O(rtol): its rounding noise moves every step size by ~1e-9 relative), so the
+            # states are compared where the times are identical: t_end above, the t_eval samples and sol(t) below
             assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
-            assert np.all(np.abs(v.y - ref.y) <= tol(ref.y) + 1e-9)
         ref2 = oracle.solve(cb, (0.0, 6.0), y0[i], method, rtol, atol, args=args[i], num_extra=0, t_eval=te,
                             dense_output=True, call_t=tq)
         w = r_te[i]
