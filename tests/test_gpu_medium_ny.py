@@ -46,7 +46,9 @@ def test_spring_chain_matches_oracle(oracle, ny, method, strict):
             # raw step rows sit at slightly different times in two implementations (the error estimate is a difference of
             # O(1) stage sums that cancels to O(rtol): its rounding noise moves every step size by ~1e-9 relative), so the
             # states are compared where the times are identical: t_end above, the t_eval samples and sol(t) below
-            assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
+            # (the FMA build rounds the estimate differently: same counts, t within 1e-4 for DOP853's heavily cancelling
+            # error combination; the strict build stays within 1e-6)
+            assert np.allclose(v.t, ref.t, rtol=1e-6 if strict else 1e-4, atol=1e-12)
         ref2 = oracle.solve(cb, (0.0, 6.0), y0[i], method, rtol, atol, args=args[i], num_extra=0, t_eval=te,
                             dense_output=True, call_t=tq)
         w = r_te[i]
