@@ -100,6 +100,7 @@ static int g_opt_dense_store = 0;     // two-pass path with dense_output: 0 = th
                                       // recomputes the step it needs), 1 = materialise every [y_old | Q] interpolant as well
 static int g_opt_events_variant = 1;  // events with store='final' and no t_eval / dense store: the VAR_EVENTS kernels (0 = VAR_FULL)
 static int g_opt_events_two_pass = 1; // ... as detection solve + one thread per triggered step (event_roots_kernel); 0 = one-pass VAR_EVENTS
+static int g_opt_events_static = 1;   // ... with the detection solve compiled for this run's event list (NVRTC, cached); 0 = generic kernel
 static int g_opt_root_batch = 12;     // measured: 8..16 is the flat optimum on the C3 workload (profiles/r01_notes.md)
 static int g_opt_ctas_per_sm = 0;
 
@@ -314,22 +315,38 @@ struct Dispatch {
     // built-in problems too (jit_id: the problem registered as a run-time right-hand side) -- instead of doubling the
     // number of precompiled instantiations for a rarely used option.
     std::string jit_defs;
+    std::string ev_defs;        // "-DCYRK_EV_STATIC=1 ...": the detection solve (VAR_EVDETECT) specialised for this run's event list
     int jit_id = -1;
+    std::string defs_for(int variant) const
+    {
+        if (variant != VAR_EVDETECT || ev_defs.empty()) return jit_defs;
+        return jit_defs.empty() ? ev_defs : jit_defs + " " + ev_defs;
+    }
     const char* name(int method, int variant) const { return (pe && jit_defs.empty()) ? pe->solve[method - 3][variant].name : (pe ? pe->struct_name : "user"); }
     cudaError_t occupancy(int method, int variant, int* ctas, int block) const
     {
-        if (pe && jit_defs.empty()) return pe->solve[method - 3][variant].occupancy(ctas, block);
-        return user_rhs_occupancy(pe ? jit_id : rhs_id, method, variant, strict, device, ctas, block, jit_defs.c_str());
+        const std::string d = defs_for(variant);
+        if (pe && d.empty()) return pe->solve[method - 3][variant].occupancy(ctas, block);
+        return user_rhs_occupancy(pe ? jit_id : rhs_id, method, variant, strict, device, ctas, block, d.c_str());
     }
     cudaError_t launch(int method, int variant, const BatchParams& p, int grid, int block, cudaStream_t s) const
     {
-        if (pe && jit_defs.empty()) return pe->solve[method - 3][variant].launch(p, grid, block, s);
-        return user_rhs_launch_solve(pe ? jit_id : rhs_id, method, variant, strict, device, p, grid, block, s, jit_defs.c_str());
+        const std::string d = defs_for(variant);
+        if (pe && d.empty()) return pe->solve[method - 3][variant].launch(p, grid, block, s);
+        return user_rhs_launch_solve(pe ? jit_id : rhs_id, method, variant, strict, device, p, grid, block, s, d.c_str());
     }
     cudaError_t prep(int method, const BatchParams& p, double* out, int grid, int block, cudaStream_t s) const
     {
         if (pe && jit_defs.empty()) return pe->prep[method - 3](p, out, grid, block, s);
         return user_rhs_launch_prep(pe ? jit_id : rhs_id, method, strict, device, p, out, grid, block, s, jit_defs.c_str());
+    }
+    int need_jit_id()
+    {
+        if (pe && jit_id < 0) {
+            jit_id = builtin_jit_id(pe->struct_name, pe->ny, pe->nextra, pe->nargs_dbl);
+            if (jit_id < 0) { set_error("cannot register built-in problem %s for run-time compilation", pe->struct_name); return -1; }
+        }
+        return 0;
     }
     int use_feature(const char* defs)
     {
@@ -801,6 +818,24 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
     };
     // Events with store='final': detection solve + one thread per triggered step (rk_core.cuh, event_roots_body)
     bool ev2 = variant == VAR_EVENTS && g_opt_events_two_pass != 0;
+    Dispatch disp_ev;                      // (a copy: the caller's dispatch stays as it is)
+    if (ev2 && g_opt_events_static) {
+        // The detection solve evaluates every event function on every booked step.  Compiled for THIS event list (ids and
+        // directions as compile-time constants) the event table's switch folds away and g_old / the hit counters live in
+        // registers; with the list as launch parameters they are local-memory arrays.  One NVRTC compilation per
+        // (problem, method, FP build, event list), cached in the process and on disk; any failure keeps the generic kernel.
+        disp_ev = *pe;
+        std::string d = "-DCYRK_EV_STATIC=1 -DCYRK_EV_N=" + std::to_string(a.n_events);
+        for (size_t e = 0; e < CYRK_MAX_EVENTS; e++) {
+            d += " -DCYRK_EV_ID" + std::to_string(e) + "=" + std::to_string(e < a.n_events ? a.event_ids[e] : 0);
+            const int dir = (e < a.n_events && a.event_dirs) ? a.event_dirs[e] : 0;
+            d += " -DCYRK_EV_DIR" + std::to_string(e) + "=" + std::to_string(dir > 0 ? 1 : dir < 0 ? -1 : 0);
+        }
+        disp_ev.ev_defs = d;
+        int ctas_probe = 0;
+        if (disp_ev.need_jit_id() == 0 && disp_ev.occupancy(a.method, VAR_EVDETECT, &ctas_probe, 128) == cudaSuccess) pe = &disp_ev;
+        else { cudaGetLastError(); g_last_error.clear(); }
+    }
     if (pick_grid(two_pass ? VAR_STEPS : (ev2 ? VAR_EVDETECT : variant))) return -1;
 
     // ---- host buffers + final-state variant + a batch worth cutting up: pipelined copy/compute path
@@ -2148,6 +2183,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "shared_args")) { g_opt_shared_args = value; return 0; }
     if (!strcmp(name, "events_variant")) { g_opt_events_variant = value; return 0; }
     if (!strcmp(name, "events_two_pass")) { g_opt_events_two_pass = value; return 0; }
+    if (!strcmp(name, "events_static")) { g_opt_events_static = value; return 0; }
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
     if (!strcmp(name, "cta_kernel")) { g_opt_cta_kernel = value; return 0; }
