@@ -88,7 +88,7 @@ WORKLOADS = {
                   descr="largey at the reference's own size (n_y=10000) RK45 rtol=1e-6 atol=1e-8, 2048 trajectories, store=final"),
 }
 # what the default N=1 run adds to the headline line: (workload, steps)
-EXTRA_WORKLOADS = [("C1", 3), ("C2full", 3), ("C3full", 3), ("C4", 3), ("C4simple", 3)]
+EXTRA_WORKLOADS = [("C1", 3), ("C2full", 3), ("C3full", 3), ("C4", 3), ("C4simple", 3), ("C4ref", 2)]
 # BASELINE sizes of configs[1] / configs[2] (4 Mi trajectories).  C2's t_eval samples are 32 KB per trajectory on the host:
 # the batch is the largest power of two whose rows fit 35 % of the host memory available right now (4 Mi needs 134 GB).
 FULL_BATCH = {"C2full": 4 * 1024 * 1024, "C3full": 4 * 1024 * 1024}
@@ -115,7 +115,7 @@ def full_batch(name):
             b //= 2
     return b
 # parity samples next to the headline one: workload -> trajectories
-PARITY_SAMPLES = {"C2full": 64 * 1024, "C3full": 64 * 1024, "C4": 64}
+PARITY_SAMPLES = {"C2full": 64 * 1024, "C3full": 64 * 1024, "C4": 64, "C4ref": 16}
 
 
 def make_inputs(w, n, seed):

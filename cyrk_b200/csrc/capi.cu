@@ -178,6 +178,7 @@ struct Handle {
     DevBuf d_st;                            // step records of the two-pass t_eval / dense path
     DevBuf d_ev_t2, d_ev_y2, d_ev_off, d_scan;   // packed (CSR) event lists: hits back to back + offsets
     DevBuf d_evq, d_evq_count;              // work items of the two-pass events path
+    DevBuf d_max;                           // [3] largest size / dense_count / ev_count of the last launch (max_counts_kernel)
     size_t evq_seen = 0;                    // items the last two-pass events solve pushed (sizes the next queue of a reused handle)
     PinBuf h_ev_off;
     bool ev_packed = false;                 // host mirrors of the event lists are CSR-packed (host-buffer solves on the thread path)
@@ -240,7 +241,7 @@ struct Handle {
         DevBuf* dbs[] = {&d_y0, &d_args, &d_tspan, &d_teval, &d_queue, &d_status, &d_size, &d_steps, &d_nrej, &d_nfev,
                          &d_tlast, &d_ylast, &d_trows, &d_yrows, &d_dense_t, &d_dense_state, &d_dense_count, &d_ev_t,
                          &d_ev_y, &d_ev_count, &d_ev_term, &d_q_t, &d_q_out, &d_q_code, &d_scratch, &d_prep, &d_rtol, &d_atol,
-                         &d_st, &d_ev_t2, &d_ev_y2, &d_ev_off, &d_scan, &d_evq, &d_evq_count};
+                         &d_st, &d_ev_t2, &d_ev_y2, &d_ev_off, &d_scan, &d_evq, &d_evq_count, &d_max};
         for (DevBuf* b : dbs) b->release();
         PinBuf* pbs[] = {&h_status, &h_size, &h_steps, &h_nrej, &h_nfev, &h_tlast, &h_ylast, &h_trows, &h_yrows,
                          &h_dense_count, &h_ev_t, &h_ev_y, &h_ev_count, &h_ev_term, &h_stage, &h_ev_off};
@@ -612,6 +613,23 @@ __global__ void teval_last_kernel(unsigned long long n_traj, const unsigned* __r
     }
 }
 
+// Largest entry of up to three per-trajectory counter arrays (rows saved, interpolants stored, event hits): what decides
+// whether an arena overflowed.  Reduced on the device: walking 12 Mi counters on one host core took 10 ms of an 85 ms step.
+__global__ void max_counts_kernel(const unsigned* __restrict__ a, unsigned long long na, const unsigned* __restrict__ b, unsigned long long nb,
+                                  const unsigned* __restrict__ c, unsigned long long nc, unsigned* __restrict__ out /*[3]*/)
+{
+    const unsigned* arr[3] = {a, b, c};
+    const unsigned long long len[3] = {na, nb, nc};
+    for (int k = 0; k < 3; k++) {
+        if (arr[k] == nullptr) continue;
+        unsigned m = 0;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < len[k]; i += (unsigned long long)gridDim.x * blockDim.x)
+            m = max(m, arr[k][i]);
+        m = __reduce_max_sync(0xffffffffu, m);
+        if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out + k, m);
+    }
+}
+
 // Event lists are ragged (the reference keeps one std::vector per event, cysolution.cpp:423-448).  On the device every
 // (trajectory, event) list owns `ev_cap` slots (default 64) but typically holds a handful of hits, so before they cross PCIe
 // the lists are packed back to back (CSR): offsets[l] .. offsets[l+1] index the hits of list l = traj * n_events + e.
@@ -679,6 +697,22 @@ __global__ void pack_events_kernel(unsigned long long n_lists, unsigned cap, uns
         t_out[dst] = t_in[src];
         for (unsigned i = 0; i < ndy; i++) y_out[dst * ndy + i] = y_in[src * ndy + i];
     }
+}
+
+// max of up to three device counter arrays into out[3]; returns with the stream synchronised
+static int counts_max(Handle* h, const unsigned* a, size_t na, const unsigned* b, size_t nb, const unsigned* c, size_t nc, unsigned* out)
+{
+    if (h->d_max.ensure(16)) return -1;
+    CU_TRY(cudaMemsetAsync(h->d_max.p, 0, 16, h->stream));
+    const size_t n = std::max(std::max(a ? na : 0, b ? nb : 0), c ? nc : 0);
+    if (n > 0) {
+        const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)device_sm_count(h->device) * 16);
+        max_counts_kernel<<<grid, 256, 0, h->stream>>>(a, na, b, nb, c, nc, h->d_max.as<unsigned>());
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaMemcpyAsync(out, h->d_max.p, 12, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
@@ -953,12 +987,10 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             if (pe->launch(a.method, VAR_STEPS, pa, grid, block, h->stream) != cudaSuccess) { cudaGetLastError(); if (g_last_error.empty()) set_error("solve kernel launch failed"); return -1; }
             h->launches++;
             CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
-            if (download(h, h->h_size, h->d_size, B * 4)) return -1;
-            h->host_valid |= 1u << HA_SIZE;
-            CU_TRY(cudaStreamSynchronize(h->stream));
+            unsigned mxs[3] = {0, 0, 0};
+            if (counts_max(h, pa.size, B, nullptr, 0, nullptr, 0, mxs)) return -1;      // (synchronises the stream)
             { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; if (getenv("CYRK_B200_DEBUG")) fprintf(stderr, "[cyrk_b200] step-recording solve: %.3f ms\n", ms); }
-            size_t mx = 0;
-            { const unsigned* sz = h->h_size.as<unsigned>(); for (size_t i = 0; i < B; i++) mx = std::max<size_t>(mx, sz[i]); }
+            const size_t mx = mxs[0];
             p_mx = mx;
             if (mx <= scap) break;
             if (force.active && force.scap) { force.need_scap = mx; return 1; }      // the parent re-plans the whole batch
@@ -1030,8 +1062,11 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             h->launches++;
         }
         CU_TRY(cudaEventRecord(h->ev_k1, h->stream));
-        if (a.n_t_eval && download(h, h->h_size, h->d_size, B * 4)) return -1;
-        if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
+        if (!device_io) {
+            if (download(h, h->h_size, h->d_size, B * 4)) return -1;
+            h->host_valid |= 1u << HA_SIZE;
+            if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
+        }
         CU_TRY(cudaStreamSynchronize(h->stream));
         { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1); h->kernel_ms += ms; if (getenv("CYRK_B200_DEBUG")) fprintf(stderr, "[cyrk_b200] step_dense (+ last row): %.3f ms, %u threads per trajectory\n", ms, q.step_threads); }
     } else {
@@ -1103,13 +1138,11 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
 
         // counters come back first: they decide whether any arena overflowed
         const bool need_check = want_rows || dense || a.n_events;
-        if (need_check) { if (download(h, h->h_size, h->d_size, B * 4)) return -1; h->host_valid |= 1u << HA_SIZE; }
-        if (dense && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
-        if (a.n_events && download(h, h->h_ev_count, h->d_ev_count, B * a.n_events * 4)) return -1;
         if (!need_check) break;
         unsigned long long evq_flag = 0;
         if (ev2) CU_TRY(cudaMemcpyAsync(&evq_flag, h->d_evq_count.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, h->stream));
-        CU_TRY(cudaStreamSynchronize(h->stream));
+        unsigned mxs[3] = {0, 0, 0};
+        if (counts_max(h, want_rows ? p.size : nullptr, B, dense ? p.dense_count : nullptr, B, a.n_events ? p.ev_count : nullptr, B * a.n_events, mxs)) return -1;
         if (ev2 && evq_flag != 0) {        // a Brent search failed (-30 / -31): the one-pass kernel reproduces what the reference does next
             ev2 = false; h->kernel_ms = 0.f;
             if (pick_grid(variant)) return -1;
@@ -1120,10 +1153,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1);
             h->kernel_ms += ms;
         }
-        size_t mx_rows = 0, mx_dense = 0, mx_ev = 0;
-        if (want_rows) { const unsigned* s = h->h_size.as<unsigned>(); for (size_t i = 0; i < B; i++) mx_rows = std::max<size_t>(mx_rows, s[i]); }
-        if (dense) { const unsigned* s = h->h_dense_count.as<unsigned>(); for (size_t i = 0; i < B; i++) mx_dense = std::max<size_t>(mx_dense, s[i]); }
-        if (a.n_events) { const unsigned* s = h->h_ev_count.as<unsigned>(); for (size_t i = 0; i < B * a.n_events; i++) mx_ev = std::max<size_t>(mx_ev, s[i]); }
+        const size_t mx_rows = mxs[0], mx_dense = mxs[1], mx_ev = mxs[2];
         const bool overflow = mx_rows > row_cap || mx_dense > dense_cap || mx_ev > ev_cap;
         ev_used = mx_ev;
         if (!overflow) break;
@@ -1171,6 +1201,12 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             download(h, h->h_ylast, h->d_ylast, B * NDY * 8))
             return -1;
         h->host_valid |= (1u << HA_STATUS) | (1u << HA_STEPS) | (1u << HA_YLAST);
+        if ((want_rows || dense || a.n_events) && !two_pass) {
+            if (download(h, h->h_size, h->d_size, B * 4)) return -1;
+            h->host_valid |= 1u << HA_SIZE;
+        }
+        if (dense && !two_pass && download(h, h->h_dense_count, h->d_dense_count, B * 4)) return -1;
+        if (a.n_events && download(h, h->h_ev_count, h->d_ev_count, B * a.n_events * 4)) return -1;
         if (want_rows) {
             if (download(h, h->h_trows, h->d_trows, B * row_cap * 8) || download(h, h->h_yrows, h->d_yrows, B * row_cap * NDY * 8))
                 return -1;
