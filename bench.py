@@ -147,11 +147,14 @@ class ClockSampler:
 
     def __init__(self, gpu):
         self.gpu, self.proc, self.lines = gpu, None, []
+        self.lo, self.hi = 0, None
 
     def start(self):
+        """Started BEFORE the warm-up steps: nvidia-smi needs up to a second before its first line on an 8-GPU box, and
+        the timed region of the headline workload is ~0.25 s (both arms)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -161,13 +164,24 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark_begin(self):
+        self.lo = len(self.lines)
+
+    def mark_end(self):
+        self.hi = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        window = self.lines[self.lo:self.hi if self.hi is not None else len(self.lines)]
+        note = "samples taken between the first timed step of the device-resident arm and the last of the end-to-end arm"
+        if not window:               # (a timed region shorter than one sampling period: the samples right around it)
+            window = self.lines[max(self.lo - 2, 0):(self.hi or 0) + 3]
+            note = "timed region shorter than one sampling period: nearest samples"
         sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -179,7 +193,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "note": note}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -286,13 +300,15 @@ def gpu_measure(c, torch, w, B, seed, local_rank, steps, warmup, barrier, sample
     common = solve_kwargs(c, w, local_rank)
 
     # ---- device-resident arm (value)
+    sampler = ClockSampler(local_rank) if sample_clocks else None
+    if sampler:
+        sampler.start()
     res = None
     for _ in range(max(warmup, 3)):
         res = c.cysolve_ivp_batch(w["rhs"], (0.0, 10.0), y0_d, args=args_d, solution_reuse=res, **common)
-    sampler = ClockSampler(local_rank) if sample_clocks else None
     barrier()
     if sampler:
-        sampler.start()
+        sampler.mark_begin()
     dev_ms, ker_ms, launches = 0.0, 0.0, 0
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -302,7 +318,6 @@ def gpu_measure(c, torch, w, B, seed, local_rank, steps, warmup, barrier, sample
         launches += res.launches
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if sampler else None
     res.close()
 
     # ---- end-to-end arm (host pinned buffers through the public API; H2D + D2H inside the timed region)
@@ -317,6 +332,10 @@ def gpu_measure(c, torch, w, B, seed, local_rank, steps, warmup, barrier, sample
         _ = float(res.y_last[0, 0])      # touch the result on the host
     barrier()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = None
+    if sampler:
+        sampler.mark_end()
+        clocks = sampler.stop()
     m = dict(B=B, dev_ms=dev_ms, ker_ms=ker_ms, launches=launches, wall_ms=wall_ms, e2e_wall_ms=e2e_wall_ms, clocks=clocks,
              h2d=int(res.h2d_bytes), d2h=int(res.d2h_bytes), e2e_launches=int(res.launches))
     # counters (fetched from the device arena on demand -- after the timed region)
