@@ -1442,13 +1442,20 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     const size_t B = a.n_traj, N = a.n_y;
     const bool device_io = (a.flags & CYRK_FLAG_DEVICE_IO) != 0;
     const bool want_rows = a.store_mode == CYRK_STORE_ROWS;
-    if (a.num_extra != 0) { set_error("the CTA-per-trajectory path does not capture extra outputs yet"); return -1; }
+    const size_t NXL = a.num_extra;
+    if (NXL != 0) {
+        // Extra outputs on this path: the functor's components n_y .. n_y + num_extra - 1, evaluated at every saved row.
+        // With t_eval, events or a dense store the reference re-evaluates the right-hand side at interpolated states and
+        // lets that leak into its stepping state; those combinations stay on the thread path.
+        if (a.rhs_id < CYRK_RHS_USER_BASE) { set_error("the built-in large problems have no extra outputs"); return -1; }
+        if (a.n_t_eval || a.n_events || a.dense_output) { set_error("extra outputs on the CTA-per-trajectory path: raw step rows / final state only (no t_eval, events or dense_output)"); return -1; }
+    }
     if (a.flags & (CYRK_FLAG_T_EVAL_PER_TRAJ | CYRK_FLAG_TOL_PER_TRAJ)) { set_error("per-trajectory t_eval / tolerances are available on the thread-per-trajectory path (n_y <= 32) only"); return -1; }
     const bool dense = a.dense_output != 0;
     const bool user_rhs = a.rhs_id >= CYRK_RHS_USER_BASE;
     if (!user_rhs && (a.n_args == 0 || a.args_len < 8)) { set_error("largey problems need args = (decay_rate, ...)"); return -1; }
     if (N > 0x7fffffffu) { set_error("n_y too large"); return -1; }
-    h->ny = N; h->nx = 0; h->ndy = N; h->q_order = 0;
+    h->ny = N; h->nx = NXL; h->ndy = N + NXL; h->q_order = 0;
     h->n_traj = B; h->n_events = a.n_events; h->n_t_eval = a.n_t_eval;
     h->dense_output = dense; h->device_io = device_io; h->cta_path = true; h->dense_from_steps = false;
     h->ev_packed = false; h->ev_total = 0;
@@ -1461,6 +1468,7 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     p.n_traj = B;
     p.n = (unsigned)N;
     p.n_pad = (unsigned)((N + 1) & ~size_t(1));
+    p.n_extra = (unsigned)NXL;
     p.max_step = a.max_step;
     p.first_step = a.first_step;
     {
@@ -1509,7 +1517,7 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         p.n_t_eval = (unsigned)a.n_t_eval;
     }
     if (h->d_status.ensure(B * 4) || h->d_size.ensure(B * 4) || h->d_steps.ensure(B * 4) || h->d_nrej.ensure(B * 4) ||
-        h->d_nfev.ensure(B * 4) || h->d_tlast.ensure(B * 8) || h->d_ylast.ensure(B * N * 8) || h->d_queue.ensure(8))
+        h->d_nfev.ensure(B * 4) || h->d_tlast.ensure(B * 8) || h->d_ylast.ensure(B * (N + NXL) * 8) || h->d_queue.ensure(8))
         return -1;
     p.status = h->d_status.as<int>(); p.size = h->d_size.as<unsigned>(); p.steps_taken = h->d_steps.as<unsigned>();
     p.n_rejected = h->d_nrej.as<unsigned>(); p.nfev = h->d_nfev.as<unsigned>();
@@ -1594,7 +1602,7 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     if (a.n_events) ev_cap = a.expected_size ? a.expected_size : 8;      // one hit record is n_y + 1 doubles: start small
     for (int pass = 0; pass < 2; pass++) {
         if (want_rows) {
-            if (h->d_trows.ensure(B * row_cap * 8) || h->d_yrows.ensure(B * row_cap * N * 8)) return -1;
+            if (h->d_trows.ensure(B * row_cap * 8) || h->d_yrows.ensure(B * row_cap * (N + NXL) * 8)) return -1;
             p.t_rows = h->d_trows.as<double>(); p.y_rows = h->d_yrows.as<double>(); p.row_cap = (unsigned)row_cap;
         }
         if (dense) {
@@ -1650,10 +1658,10 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     h->row_cap = row_cap; h->dense_cap = dense_cap; h->ev_cap = ev_cap;
     if (!device_io) {
         if (download(h, h->h_status, h->d_status, B * 4) || download(h, h->h_steps, h->d_steps, B * 4) ||
-            download(h, h->h_ylast, h->d_ylast, B * N * 8))
+            download(h, h->h_ylast, h->d_ylast, B * (N + NXL) * 8))
             return -1;
         h->host_valid |= (1u << HA_STATUS) | (1u << HA_STEPS) | (1u << HA_YLAST);
-        if (want_rows && (download(h, h->h_trows, h->d_trows, B * row_cap * 8) || download(h, h->h_yrows, h->d_yrows, B * row_cap * N * 8)))
+        if (want_rows && (download(h, h->h_trows, h->d_trows, B * row_cap * 8) || download(h, h->h_yrows, h->d_yrows, B * row_cap * (N + NXL) * 8)))
             return -1;
         if (a.n_events && (download(h, h->h_ev_t, h->d_ev_t, B * a.n_events * ev_cap * 8) ||
                            download(h, h->h_ev_y, h->d_ev_y, B * a.n_events * ev_cap * N * 8) ||
@@ -1752,6 +1760,10 @@ static int solve_impl(Handle* h, const SolveArgs& a)
     g_last_error.clear();
     if (!make_dispatch(a.rhs_id, fp, a.device, &disp)) { set_error("unknown right-hand side id %d", a.rhs_id); return -1; }
     if (a.rhs_id >= CYRK_RHS_USER_BASE && disp.ny == 0) {        // user right-hand side registered for large systems
+        if ((size_t)disp.nextra != a.num_extra) {
+            set_error("right-hand side %d produces %d extra outputs but num_extra = %zu", a.rhs_id, disp.nextra, a.num_extra);
+            return -1;
+        }
         if (solve_cta_path(h, a, fp)) return -1;
         h->solved = true;
         return 0;

@@ -385,17 +385,30 @@ struct Cta2Solver {
 
     CYRK_DI void save_row_from_ybuf(const CtaParams& p, unsigned long long traj, double t)
     {
-        if (p.t_rows != nullptr && size < p.row_cap) {
+        const unsigned ndy = n + p.n_extra;
+        const bool row = p.t_rows != nullptr && size < p.row_cap;
+        if (row) {
             const unsigned long long r = traj * p.row_cap + size;
             if (tid == 0) p.t_rows[r] = t;
-            double* dst = p.y_rows + r * n;
+            double* dst = p.y_rows + r * ndy;
 #pragma unroll
             for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) dst[i] = ybuf[i]; }
+        }
+        if (p.n_extra > 0) {
+            // extra outputs of this row = components n.. of the functor at (t, y): what the right-hand-side call that
+            // produced dy_now wrote to dy[n_y:] (same inputs -> same values).  ybuf is complete and visible here: the last
+            // stage evaluation read it after a barrier.  (No t_eval / events / dense store with extras on this path.)
+            for (unsigned j = tid; j < p.n_extra; j += T) {
+                const double v = Prob::eval(n + j, t, ybuf, n, args, aux);
+                if (row) p.y_rows[(traj * p.row_cap + size) * ndy + n + j] = v;
+                p.y_last[traj * ndy + n + j] = v;
+            }
+            __syncthreads();         // the functor read other threads' components of ybuf: nobody overwrites them before this
         }
         if (p.n_t_eval > 0) {
             // raw steps saved after t_eval has finished: keep y_last on the row t_last belongs to
             // (without t_eval the final write-out stores it once)
-            double* yl = p.y_last + traj * n;
+            double* yl = p.y_last + traj * ndy;
 #pragma unroll
             for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) yl[i] = ybuf[i]; }
         }
@@ -752,7 +765,7 @@ struct Cta2Solver {
         }
         // ---- results
         if (p.n_t_eval == 0) {
-            double* yl = p.y_last + traj * n;
+            double* yl = p.y_last + traj * (n + p.n_extra);         // (the extras of the last saved row are already there)
 #pragma unroll
             for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) yl[i] = ybuf[i]; }
         } else if (size == 0) {

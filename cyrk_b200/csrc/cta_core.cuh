@@ -256,11 +256,21 @@ struct CtaSolver {
 
     CYRK_DI void save_row(const CtaParams& p, unsigned long long traj, double t, const double* y)
     {
-        if (p.t_rows != nullptr && size < p.row_cap) {
+        const unsigned ndy = n + p.n_extra;
+        const bool row = p.t_rows != nullptr && size < p.row_cap;
+        if (p.n_extra > 0) {               // extra outputs of this row: the functor's components n .. (see cta2_core.cuh)
+            for (unsigned j = threadIdx.x; j < p.n_extra; j += blockDim.x) {
+                const double v = Prob::eval(n + j, t, y, n, args, aux);
+                if (row) p.y_rows[(traj * p.row_cap + size) * ndy + n + j] = v;
+                p.y_last[traj * ndy + n + j] = v;
+            }
+            __syncthreads();         // (the functor read other threads' components of y)
+        }
+        if (row) {
             const unsigned long long r = traj * p.row_cap + size;
             if (threadIdx.x == 0) p.t_rows[r] = t;
-            double* dst = p.y_rows + r * n;
-            if ((n & 1u) == 0u) {          // 128-bit stores: rows are 16-byte aligned when n is even
+            double* dst = p.y_rows + r * ndy;
+            if (((n | ndy) & 1u) == 0u) {  // 128-bit stores: rows are 16-byte aligned when the row width is even
                 double2* d2 = reinterpret_cast<double2*>(dst);
                 for (unsigned i = threadIdx.x; i < (n >> 1); i += blockDim.x) d2[i] = make_double2(y[2 * i], y[2 * i + 1]);
             } else {
@@ -268,7 +278,7 @@ struct CtaSolver {
             }
         }
         if (p.n_t_eval > 0) {      // raw steps saved after t_eval has finished (quirk 6): y_last follows t_last
-            double* yl = p.y_last + traj * n;
+            double* yl = p.y_last + traj * ndy;
             for (unsigned i = threadIdx.x; i < n; i += blockDim.x) yl[i] = y[i];
         }
         t_last = t;
@@ -408,7 +418,7 @@ struct CtaSolver {
         }
         // ---- results
         if (p.n_t_eval == 0) {
-            double* yl = p.y_last + traj * n;
+            double* yl = p.y_last + traj * (n + p.n_extra);
             for (unsigned i = threadIdx.x; i < n; i += blockDim.x) yl[i] = y_now[i];
         } else if (size == 0) {
             double* yl = p.y_last + traj * n;

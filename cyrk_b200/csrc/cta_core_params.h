@@ -7,6 +7,8 @@ struct CtaParams {
     unsigned long long n_traj;
     unsigned n;                  // n_y
     unsigned n_pad;              // n rounded up to a multiple of 2 (128-bit accesses)
+    unsigned n_extra;            // extra outputs: the functor's components n .. n + n_extra - 1, evaluated at every SAVED row
+                                 // (the reference captures dy[n_y:], cysolver.cpp:945-961); rows and y_last are n + n_extra wide
     const double* y0;            // [n_traj][n]
     const char*   args;          // per-trajectory blob of args_stride bytes, or shared (stride 0)
     unsigned      args_stride;

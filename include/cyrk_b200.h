@@ -103,8 +103,10 @@ int cyrk_b200_rhs_info(int rhs_id, size_t* n_y, size_t* n_extra, size_t* args_by
  *     __device__ double <entry>_event(int id, double t, const double* y_and_extras, const char* args);
  * mirroring DiffeqFuncType / EventFunc (c_common.hpp:218-220, c_events.hpp:9); a pre-eval hook is
  * just another __device__ function the source calls.  LARGE systems (n_y == 0 here; the size comes with each solve
- * call; CTA-per-trajectory path, no extra outputs) are written component-wise instead:
+ * call; CTA-per-trajectory path) are written component-wise instead:
  *     __device__ double <entry>(unsigned i, double t, const double* y, unsigned n, const char* args);      -> dy_i
+ *         (i >= n: extra output i - n, CyRK's dy[n_y:]; asked for at saved rows only; extra outputs on this path
+ *          come with raw step rows / the final state, not with t_eval, events or dense_output)
  *     __device__ double <entry>_event(int id, double t, const double* y, unsigned n, const char* args);     -> g_id
  * Returns an id >= CYRK_RHS_USER_BASE, or -1
  * (compile log in `log`).  Compiled modules are cached by source hash per process and on disk (see below). */

@@ -128,11 +128,23 @@ __device__ double chain(unsigned i, double t, const double* y, unsigned n, const
 '''
 
 
+CHAIN_X_SRC = r'''
+// the same chain with two extra outputs (CyRK's dy[n_y:], cysolver_test.pyx:42-57): the functor answers i = n and n + 1
+__device__ double chainx(unsigned i, double t, const double* y, unsigned n, const char* args) {
+    const double r = ((const double*)args)[0];
+    if (i == n) return y[0] * y[n - 1] + t;               // extra 0
+    if (i == n + 1) return r * (y[1] - y[0]);             // extra 1
+    const double left = i > 0 ? y[i - 1] : 0.0, right = i + 1 < n ? y[i + 1] : 0.0;
+    return r * (left - 2.0 * y[i] + right) + 0.1 * sin(t);
+}
+'''
+
+
 def test_large_user_rhs_compiles_on_cpu():
     u = c.UserRHS(CHAIN_SRC, "chain", n_y=0, args_bytes=8)
     assert u.rhs_id >= 1000
-    with pytest.raises(c.CyrkB200Error):
-        c.UserRHS(CHAIN_SRC, "chain", n_y=0, n_extra=1)          # no extras on the large path yet
+    ux = c.UserRHS(CHAIN_X_SRC, "chainx", n_y=0, n_extra=2, args_bytes=8)      # components n, n+1 are extra outputs
+    assert ux.rhs_id >= 1000 and ux.rhs_id != u.rhs_id
 
 
 @pytest.mark.gpu
@@ -166,6 +178,44 @@ def test_large_user_rhs_matches_oracle(oracle, method, n):
             assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken)
             assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
             assert np.all(np.abs(v.y - ref.y) <= 10 * 1e-6 * np.abs(ref.y) + 10 * 1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,n", [("RK23", 96), ("RK45", 700), ("DOP853", 1100), ("RK45", 5000)])
+def test_large_user_rhs_with_extra_outputs(oracle, method, n):
+    """Extra outputs on the CTA-per-trajectory path (register-resident kernel for n_y <= 4096, slab kernel above): every
+    saved row carries dy[n_y:] of the right-hand-side call at that row (cysolver.cpp:968-972 save_data), rows are
+    n_y + num_extra wide like CySolverResult::solution."""
+    import ctypes as C
+    B = 3
+    u = c.UserRHS(CHAIN_X_SRC, "chainx", n_y=0, n_extra=2, args_bytes=8)
+    rng = np.random.default_rng(29)
+    y0 = rng.uniform(0.0, 1.0, (B, n))
+    rates = np.array([[0.5], [0.8], [1.1]])
+
+    @oracle.DIFFEQ_FN
+    def cb(dy, t, y, args, pre):
+        yy = np.ctypeslib.as_array(y, shape=(n,))
+        r = C.cast(args, C.POINTER(C.c_double))[0]
+        left = np.concatenate([[0.0], yy[:-1]])
+        right = np.concatenate([yy[1:], [0.0]])
+        out = np.concatenate([r * (left - 2.0 * yy + right) + 0.1 * np.sin(t), [yy[0] * yy[n - 1] + t, r * (yy[1] - yy[0])]])
+        C.memmove(dy, out.ctypes.data, 8 * (n + 2))
+
+    for store in ("rows", "final"):
+        r = c.cysolve_ivp_batch(u, (0.0, 2.0), y0, method=method, args=rates, rtol=1e-6, atol=1e-9, num_extra=2, store=store)
+        assert r.num_y == n and r.num_dy == n + 2
+        for i in range(B):
+            ref = oracle.solve(cb, (0.0, 2.0), y0[i], method, 1e-6, 1e-9, args=rates[i], num_extra=2)
+            assert (int(r.status[i]), int(r.size[i]), int(r.steps_taken[i]), int(r.nfev[i])) == (ref.status, ref.size, ref.steps_taken, ref.nfev)
+            tol = 10 * 1e-6 * np.abs(ref.y) + 10 * 1e-9
+            assert np.all(np.abs(r.y_last[i] - ref.y[:, -1]) <= tol[:, -1] + 1e-12)
+            if store == "rows":
+                v = r[i]
+                assert v.y.shape == (n + 2, ref.size) and np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
+                assert np.all(np.abs(v.y - ref.y) <= tol + 1e-9)
+    with pytest.raises(c.CyrkB200Error, match="raw step rows / final state only"):
+        c.cysolve_ivp_batch(u, (0.0, 2.0), y0, method=method, args=rates, num_extra=2, t_eval=np.linspace(0, 2, 5))
 
 
 CHAIN_EV_SRC = CHAIN_SRC + r'''
