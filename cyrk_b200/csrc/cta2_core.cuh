@@ -385,7 +385,7 @@ struct Cta2Solver {
 
     CYRK_DI void save_row_from_ybuf(const CtaParams& p, unsigned long long traj, double t)
     {
-        const unsigned ndy = n + p.n_extra;
+        const unsigned ndy = Prob::HAS_EXTRAS ? n + p.n_extra : n;
         const bool row = p.t_rows != nullptr && size < p.row_cap;
         if (row) {
             const unsigned long long r = traj * p.row_cap + size;
@@ -394,7 +394,7 @@ struct Cta2Solver {
 #pragma unroll
             for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) dst[i] = ybuf[i]; }
         }
-        if (p.n_extra > 0) {
+        if constexpr (Prob::HAS_EXTRAS) {
             // extra outputs of this row = components n.. of the functor at (t, y): what the right-hand-side call that
             // produced dy_now wrote to dy[n_y:] (same inputs -> same values).  ybuf is complete and visible here: the last
             // stage evaluation read it after a barrier.  (No t_eval / events / dense store with extras on this path.)
@@ -765,7 +765,7 @@ struct Cta2Solver {
         }
         // ---- results
         if (p.n_t_eval == 0) {
-            double* yl = p.y_last + traj * (n + p.n_extra);         // (the extras of the last saved row are already there)
+            double* yl = p.y_last + traj * (Prob::HAS_EXTRAS ? n + p.n_extra : n);   // (the extras of the last saved row are already there)
 #pragma unroll
             for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) yl[i] = ybuf[i]; }
         } else if (size == 0) {

@@ -256,9 +256,9 @@ struct CtaSolver {
 
     CYRK_DI void save_row(const CtaParams& p, unsigned long long traj, double t, const double* y)
     {
-        const unsigned ndy = n + p.n_extra;
+        const unsigned ndy = Prob::HAS_EXTRAS ? n + p.n_extra : n;
         const bool row = p.t_rows != nullptr && size < p.row_cap;
-        if (p.n_extra > 0) {               // extra outputs of this row: the functor's components n .. (see cta2_core.cuh)
+        if constexpr (Prob::HAS_EXTRAS) {               // extra outputs of this row: the functor's components n .. (see cta2_core.cuh)
             for (unsigned j = threadIdx.x; j < p.n_extra; j += blockDim.x) {
                 const double v = Prob::eval(n + j, t, y, n, args, aux);
                 if (row) p.y_rows[(traj * p.row_cap + size) * ndy + n + j] = v;
@@ -418,7 +418,7 @@ struct CtaSolver {
         }
         // ---- results
         if (p.n_t_eval == 0) {
-            double* yl = p.y_last + traj * (n + p.n_extra);
+            double* yl = p.y_last + traj * (Prob::HAS_EXTRAS ? n + p.n_extra : n);
             for (unsigned i = threadIdx.x; i < n; i += blockDim.x) yl[i] = y_now[i];
         } else if (size == 0) {
             double* yl = p.y_last + traj * n;
