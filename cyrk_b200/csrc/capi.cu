@@ -1534,7 +1534,9 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     // thread it spills (7.9 vs 6.1 ms): that one case stays on the shared-memory/slab kernel unless a feature only the
     // register-resident kernel has (stored dense output, events) is requested.
     const bool dop_c8 = a.method == CYRK_METHOD_DOP853 && N > (size_t)4 * cta2_max_block && !a.dense_output && a.n_events == 0;
-    const bool use_cta2 = g_opt_cta_kernel != 1 && N <= (size_t)8 * cta2_max_block && !(dop_c8 && g_opt_cta_kernel == 0);
+    bool whole_vector = false;           // user system in the whole-vector form: one thread evaluates it (slab kernel only)
+    if (user_rhs) { int uny = 0, unx = 0, una = 0, une = 0; if (user_rhs_info(a.rhs_id, &uny, &unx, &una, &une) == 0) whole_vector = uny > CYRK_MAX_NY; }
+    const bool use_cta2 = !whole_vector && g_opt_cta_kernel != 1 && N <= (size_t)8 * cta2_max_block && !(dop_c8 && g_opt_cta_kernel == 0);
     int cta2_C = 0;
     int block, grid;
     size_t smem;
@@ -1759,7 +1761,8 @@ static int solve_impl(Handle* h, const SolveArgs& a)
     Dispatch disp;
     g_last_error.clear();
     if (!make_dispatch(a.rhs_id, fp, a.device, &disp)) { set_error("unknown right-hand side id %d", a.rhs_id); return -1; }
-    if (a.rhs_id >= CYRK_RHS_USER_BASE && disp.ny == 0) {        // user right-hand side registered for large systems
+    if (a.rhs_id >= CYRK_RHS_USER_BASE && (disp.ny == 0 || disp.ny > CYRK_MAX_NY)) {     // user right-hand side registered for large systems
+        if (disp.ny != 0 && (size_t)disp.ny != a.n_y) { set_error("right-hand side %d has n_y = %d but y0 has n_y = %zu", a.rhs_id, disp.ny, a.n_y); return -1; }
         if ((size_t)disp.nextra != a.num_extra) {
             set_error("right-hand side %d produces %d extra outputs but num_extra = %zu", a.rhs_id, disp.nextra, a.num_extra);
             return -1;

@@ -85,9 +85,13 @@ struct CtaSolver {
     CYRK_DI double* K(int j) const { return vecp(V_K0 + j); }
 
     // dy[i] = f_i(t, y) for the whole vector; y must be complete (caller syncs before and after)
+    // A problem given in the reference's WHOLE-VECTOR form -- void f(dy, t, y, args), c_common.hpp:218-220 -- cannot be
+    // split over threads: one thread evaluates it into the derivative vector (the stage arithmetic around it stays
+    // parallel).  This is how user systems with n_y > CYRK_MAX_NY keep the signature they have for small n_y.
     CYRK_DI void eval_rhs(double t, const double* y, double* dy)
     {
-        for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dy[i] = Prob::eval(i, t, y, n, args, aux);
+        if constexpr (Prob::WHOLE_VECTOR) { if (threadIdx.x == 0) Prob::eval_all(dy, t, y, args); }
+        else for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dy[i] = Prob::eval(i, t, y, n, args, aux);
         nfev++;
         __syncthreads();
     }
@@ -384,9 +388,7 @@ struct CtaSolver {
                         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) in[i] = yo[i] + dot_k<XRow<2>, 15>(i, XRow<2>{}) * step;
                         __syncthreads();
                         double* spare = aux + (unsigned long long)p.n_pad;
-                        for (unsigned i = threadIdx.x; i < n; i += blockDim.x) spare[i] = Prob::eval(i, t_old + (step * LdDop::cx(2)), in, n, args, aux);
-                        nfev++;
-                        __syncthreads();
+                        eval_rhs(t_old + (step * LdDop::cx(2)), in, spare);
                         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) in[i] = spare[i];
                         __syncthreads();
                     }

@@ -12,6 +12,7 @@ namespace cyrk {
 struct ProbLargeY {
     static constexpr bool INLINE_EVAL = CYRK_LARGEY_INLINE;     // register-resident CTA kernel: call vs inline the functor
     static constexpr bool HAS_EXTRAS = false;                   // no extra outputs: the row-saving code carries none of it
+    static constexpr bool WHOLE_VECTOR = false;                 // component-wise functor
     // r_i = r * 0.9999^(i+1) by SEQUENTIAL multiplication like the reference loop (one thread; shared args are
     // prepared once per CTA), so the rates are bit-identical to the reference's.
     __device__ __forceinline__ static void prepare(const char* args, unsigned n, double* aux, bool reuse)
@@ -45,6 +46,7 @@ struct ProbLargeY {
 struct ProbLargeYSimple {
     static constexpr bool INLINE_EVAL = true;
     static constexpr bool HAS_EXTRAS = false;
+    static constexpr bool WHOLE_VECTOR = false;
     __device__ __forceinline__ static void prepare(const char*, unsigned, double*, bool) { __syncthreads(); }
     __device__ __forceinline__ static double event(int id, double t, const double* y, unsigned, const char* args)
     {

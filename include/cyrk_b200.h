@@ -107,6 +107,9 @@ int cyrk_b200_rhs_info(int rhs_id, size_t* n_y, size_t* n_extra, size_t* args_by
  *     __device__ double <entry>(unsigned i, double t, const double* y, unsigned n, const char* args);      -> dy_i
  *         (i >= n: extra output i - n, CyRK's dy[n_y:]; asked for at saved rows only; extra outputs on this path
  *          come with raw step rows / the final state, not with t_eval, events or dense_output)
+ * A whole-vector <entry>(dy, t, y, args) with n_y > 32 is accepted too (same signature as for small systems; no extras /
+ * events): it runs on the CTA-per-trajectory path with ONE thread evaluating the function per stage -- correct, and fine
+ * for cheap right-hand sides; the component-wise form is the one that scales.
  *     __device__ double <entry>_event(int id, double t, const double* y, unsigned n, const char* args);     -> g_id
  * Returns an id >= CYRK_RHS_USER_BASE, or -1
  * (compile log in `log`).  Compiled modules are cached by source hash per process and on disk (see below). */

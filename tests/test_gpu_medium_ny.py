@@ -11,6 +11,34 @@ from medium_ny import chain_callback, chain_inputs, chain_source
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("method", ["RK23", "RK45", "DOP853"])
+@pytest.mark.parametrize("ny", [34, 48, 200])
+def test_whole_vector_signature_above_32_components(oracle, ny, method):
+    """The SAME source form -- void f(dy, t, y, args), the reference's DiffeqFuncType -- keeps working past the
+    thread-per-trajectory limit: such a system runs on the CTA-per-trajectory path with one thread evaluating the function
+    per stage (cta_core.cuh, Prob::WHOLE_VECTOR)."""
+    m = ny // 2
+    u = c.UserRHS(chain_source(m), f"chain{ny}", n_y=ny, args_bytes=16)
+    B = 6
+    y0, args = chain_inputs(m, B, 70 + ny)
+    cb = chain_callback(oracle, m)
+    rtol, atol = (1e-5, 1e-8) if method == "RK23" else (1e-8, 1e-10)
+    te = np.linspace(0.0, 4.0, 9)
+    for t_eval in (None, te):
+        r = c.cysolve_ivp_batch(u, (0.0, 4.0), y0, method=method, args=args, rtol=rtol, atol=atol, t_eval=t_eval,
+                                expected_size=2048, strict_fp=True)
+        for i in range(B):
+            ref = oracle.solve(cb, (0.0, 4.0), y0[i], method, rtol, atol, args=args[i], num_extra=0, t_eval=t_eval)
+            v = r[i]
+            assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken)
+            assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
+            tol = 10 * rtol * np.abs(ref.y) + 10 * atol
+            if t_eval is None:
+                assert np.all(np.abs(v.y[:, -1] - ref.y[:, -1]) <= tol[:, -1])
+            else:
+                assert np.all(np.abs(v.y - ref.y) <= tol)
+
+
 @pytest.mark.parametrize("strict", [True, False], ids=["strict", "fma"])
 @pytest.mark.parametrize("method", ["RK23", "RK45", "DOP853"])
 @pytest.mark.parametrize("ny", [4, 8, 16, 32])

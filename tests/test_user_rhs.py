@@ -48,8 +48,9 @@ def test_compile_cache_and_error_log():
     assert (a.value, b.value, d.value) == (2, 0, 32)
     with pytest.raises(c.CyrkB200Error, match="undefined"):
         c.UserRHS("__device__ void bad(double* dy, double t, const double* y, const char* a) { dy[0] = nope; }", "bad", n_y=1)
-    with pytest.raises(c.CyrkB200Error):
-        c.UserRHS(LV_SRC, "my_lv", n_y=64)
+    assert c.UserRHS(LV_SRC, "my_lv", n_y=64, args_bytes=32).rhs_id >= 1000   # whole-vector form above 32: CTA path, one thread evaluates it
+    with pytest.raises(c.CyrkB200Error, match="component-wise"):
+        c.UserRHS(LV_SRC, "my_lv", n_y=64, n_extra=1, args_bytes=32)
 
 
 @pytest.mark.gpu
