@@ -87,6 +87,7 @@ void registry_init()
 static int g_opt_refill_min = 0;      // 0 = automatic (1 with prep, 4 without)
 static int g_opt_prep = -1;           // -1 = automatic (n_traj >= 2 Mi), 1 = always, 0 = never
 static int g_opt_block = 0;            // threads per CTA of the thread-per-trajectory kernels; 0 = pick by occupancy (128 or 96)
+static int g_opt_cta2_wide = 1;       // register-resident CTA kernel above 2048 components: 16 per thread x 256 threads
 static int g_opt_cta_smem_vecs = -1;  // CTA path: working vectors kept in shared memory (-1 = as many as fit)
 static int g_opt_cta_block = 0;       // CTA path: threads per CTA (0 = by n_y)
 static int g_opt_pipe_taper = 1;       // pipelined host-I/O path: short first / last chunks
@@ -1563,13 +1564,15 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     }
     if (use_cta2) {
         cta2_C = N <= (size_t)cta2_max_block ? 1 : N <= (size_t)2 * cta2_max_block ? 2 : N <= (size_t)4 * cta2_max_block ? 4 : 8;
-        block = (int)(((N + cta2_C - 1) / cta2_C + 31) / 32 * 32);
+        // above 2048 components: 256 threads x 16 components instead of 512 x 8 (cta_core_params.h); built-in RK23 / RK45
+        if (cta2_C == 8 && g_opt_cta2_wide && a.method != CYRK_METHOD_DOP853 && !user_rhs) cta2_C = 16;
+        block = cta2_block(N, cta2_C);
         const size_t V = (size_t)block * cta2_C;
         const int nkd = cta2_nkd(a.method);
-        smem = (size_t)(3 + cta2_nsm(nkd, cta2_C)) * V * 8;
+        smem = (size_t)cta2_smem_vectors(nkd, cta2_C) * V * 8;
         if (smem + 1024 > (size_t)optin) { set_error("internal: CTA kernel shared-memory layout exceeds the device limit"); return -1; }
         // registers: the kernel is compiled for <= 128 per thread (__launch_bounds__(512, 1))
-        const size_t by_regs = std::max<size_t>(1, (size_t)65536 / ((size_t)128 * block));
+        const size_t by_regs = std::max<size_t>(1, (size_t)65536 / ((size_t)(cta2_C >= 16 ? 255 : 128) * block));
         const size_t by_smem = std::max<size_t>(1, (size_t)smem_per_sm / (smem + 2048));
         const int per_sm = (int)std::min<size_t>({(size_t)8, by_regs, by_smem});
         grid = (int)std::min<unsigned long long>((unsigned long long)device_sm_count(h->device) * per_sm, B);
@@ -1837,10 +1840,12 @@ __global__ void ensemble_final_kernel(const double* __restrict__ partial, int nb
 // FP64 throughput probe: 8 independent DFMA chains per thread
 // ------------------------------------------------------------------------------------------------
 // the production build's sin/cos (rk_core.cuh psin/pcos), one thread per element, for the accuracy test
-__global__ void sincos_probe_kernel(const double* __restrict__ x, double* __restrict__ s, double* __restrict__ c, size_t n)
+__global__ void sincos_probe_kernel(const double* __restrict__ x, double* __restrict__ s, double* __restrict__ c, size_t n, int mode)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { s[i] = cyrk::fast::psin(x[i]); c[i] = cyrk::fast::pcos(x[i]); }
+    if (i >= n) return;
+    if (mode == 0) { s[i] = cyrk::fast::psin(x[i]); c[i] = cyrk::fast::pcos(x[i]); }
+    else { s[i] = cyrk::fast::psin_pi(x[i]); c[i] = cyrk::fast::psin_fast(x[i]); }     // the check-free variants (|x| <= 1e5)
 }
 
 __global__ void fp64_probe_kernel(double* out, int iters, double a, double b)
@@ -2236,6 +2241,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "events_two_pass")) { g_opt_events_two_pass = value; return 0; }
     if (!strcmp(name, "events_static")) { g_opt_events_static = value; return 0; }
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
+    if (!strcmp(name, "cta2_wide")) { g_opt_cta2_wide = value; return 0; }
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
     if (!strcmp(name, "cta_kernel")) { g_opt_cta_kernel = value; return 0; }
     if (!strcmp(name, "pipe_taper")) { g_opt_pipe_taper = value; return 0; }
@@ -2248,12 +2254,14 @@ int cyrk_b200_set_option(const char* name, int value)
 int cyrk_b200_debug_sincos(const double* x, double* sin_out, double* cos_out, size_t n, int device)
 {
     DeviceGuard guard;
+    const int mode = device >> 8;            // debug entry point: bits 8.. of `device` select the function pair (see the kernel)
+    device &= 0xff;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_error("no CUDA device %d", device); return -1; }
     double *dx = nullptr, *ds = nullptr, *dc = nullptr;
     int rc = -1;
     if (cudaMalloc(&dx, n * 8) == cudaSuccess && cudaMalloc(&ds, n * 8) == cudaSuccess && cudaMalloc(&dc, n * 8) == cudaSuccess &&
         cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice) == cudaSuccess) {
-        sincos_probe_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dx, ds, dc, n);
+        sincos_probe_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dx, ds, dc, n, mode);
         if (cudaMemcpy(sin_out, ds, n * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
             cudaMemcpy(cos_out, dc, n * 8, cudaMemcpyDeviceToHost) == cudaSuccess)
             rc = 0;

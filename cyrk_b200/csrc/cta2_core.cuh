@@ -27,14 +27,18 @@
 // this path (the host shim rejects it): extra outputs.
 #pragma once
 
-#ifndef CYRK_EVAL_GROUP
-#define CYRK_EVAL_GROUP 1      // components per right-hand-side call on the register-resident CTA kernel
+#ifndef CYRK_EVAL_UNROLL
+#define CYRK_EVAL_UNROLL 4     // unroll factor of the per-thread component loop of a right-hand-side evaluation
 #endif
 #include "rk_core.cuh"
 #include "cta_core_params.h"
 
 namespace cyrk {
 namespace CYRK_FP_NS {
+
+template <class...> struct VoidT { typedef void type; };
+template <class P, class = void> struct HasTprep { static constexpr bool value = false; };
+template <class P> struct HasTprep<P, typename VoidT<decltype(P::tprep(0.0, (const char*)nullptr))>::type> { static constexpr bool value = true; };
 
 // EVENTS: compiled with the event machinery (a separate instantiation: its per-event state and extra pointers would
 // otherwise push the event-free kernel over its 128-register budget).
@@ -57,14 +61,14 @@ struct Cta2Solver {
 
     double yo[C];
     double kr[NREG > 0 ? NREG : 1][C];
-    double* buf0; double* buf1;  // stage-input buffers (shared memory), V doubles each (no run-time indexed member arrays:
-                                 // they would drag the whole solver state into local memory)
-    double* ybuf;                // the buffer that holds y_now (last y_new computed, or y0; the terminal state after an event)
-    const double* ystep;         // y_new of the step just taken (the interpolant's end point; == ybuf except after termination)
+    // Shared memory, V doubles per vector: [buf 0 | buf 1 | aux | K_NREG .. K_{NREG+NSM-1}] (+ one staging vector when
+    // NSM == 0).  The solver keeps ONE base pointer and small indices instead of a pointer per vector: with C >= 2 every
+    // address is base + thread offset + immediate, and the 64-bit pointers do not compete with the state for registers.
+    double* sm;
+    int yb;                      // stage-input buffer that holds y_now (last y_new computed, or y0; the terminal state after an event)
+    int ys;                      // buffer with y_new of the step just taken (the interpolant's end point; == yb except after termination)
     double* gsh;                 // shared memory [1 + CYRK_MAX_EVENTS]: event values published by thread 0
     double* xbuf;                // global scratch vector [V]: the interpolated state at xb during a root search
-    double* aux;                 // [V] shared memory
-    double* ksm;                 // [NSM][V] shared memory
     double* kgl;                 // [NGL][V] global slab
     double (*red)[32];
     int red_phase;
@@ -78,18 +82,32 @@ struct Cta2Solver {
     bool uni_tol;
     double rt0, at0;
 
-    CYRK_DI unsigned comp(int c) const { return tid + (unsigned)c * T; }
+    // With more than one component per thread the CTA always has cta2_threads(C) threads, so the component stride and
+    // the vector length are compile-time: every shared-memory access is [thread base + immediate].
+    static constexpr unsigned TB = (unsigned)cta2_threads(C);
+    CYRK_DI unsigned comp(int c) const { if constexpr (C >= 2) return tid + (unsigned)c * TB; else return tid; }
+    CYRK_DI unsigned vlen() const { if constexpr (C >= 2) return (unsigned)C * TB; else return V; }
+    CYRK_DI double* buf(int b) const { return sm + (b ? vlen() : 0u); }
+    CYRK_DI double* ybuf() const { return buf(yb); }
+    CYRK_DI const double* ystep() const { return buf(ys); }
+    CYRK_DI double* aux() const { return sm + 2u * vlen(); }
+    CYRK_DI double* ksm() const { return sm + 3u * vlen(); }
+    CYRK_DI double* stg() const { return sm + 3u * vlen(); }      // staging vector of eval_rhs: K_NREG's, or its own when NSM == 0
+    template <int J> CYRK_DI double* kvec() const        // where K_J lives when it is not in registers
+    {
+        static_assert(J >= NREG, "K_J is register-resident");
+        if constexpr (J < NREG + NSM) return ksm() + (unsigned)(J - NREG) * vlen();
+        else return kgl + (unsigned long long)(J - NREG - NSM) * vlen();
+    }
     template <int J> CYRK_DI double kget(int c) const
     {
         if constexpr (J < NREG) return kr[J][c];
-        else if constexpr (J < NREG + NSM) return ksm[(unsigned)(J - NREG) * V + comp(c)];
-        else return kgl[(unsigned long long)(J - NREG - NSM) * V + comp(c)];
+        else return kvec<J>()[comp(c)];
     }
     template <int J> CYRK_DI void kset(int c, double v)
     {
         if constexpr (J < NREG) kr[J][c] = v;
-        else if constexpr (J < NREG + NSM) ksm[(unsigned)(J - NREG) * V + comp(c)] = v;
-        else kgl[(unsigned long long)(J - NREG - NSM) * V + comp(c)] = v;
+        else kvec<J>()[comp(c)] = v;
     }
     CYRK_DI double rtol_at(const CtaParams& p, unsigned i) const { return uni_tol ? rt0 : p.rtol[i]; }
     CYRK_DI double atol_at(const CtaParams& p, unsigned i) const { return uni_tol ? at0 : p.atol[i]; }
@@ -135,55 +153,64 @@ struct Cta2Solver {
     template <int R> struct XRow { CYRK_HD static constexpr double get(int j) { return TabDOP853::ax(R, j); } CYRK_DI static double ld(int j) { return LdDop::ax(R, j); } };
     template <int R> struct DRow { CYRK_HD static constexpr double get(int j) { return TabDOP853::d(R, j); } CYRK_DI static double ld(int j) { return LdDop::d(R, j); } };
 
-    // One component of the right-hand side as a real function call: inlined, the functor would be replicated
-    // (stages + 1) * C times per attempt -- the first build of this kernel was 19 456 instructions (311 KB) for
-    // largey/RK45/C=8 and spent 30 % of its stall samples waiting for instruction fetch (profiles/r01_notes.md).
-    // Problems whose functor is a handful of instructions say so with `static constexpr bool INLINE_EVAL = true`.
-    static __device__ __noinline__ double eval_call(unsigned i, double t, const double* in, unsigned n, const char* args, const double* aux)
+    // K_J = f(t, in) for the components this thread owns; `in` must be complete (the caller has synchronised).
+    // The functor is inlined into a ROLLED loop over the thread's components (unrolled CYRK_EVAL_UNROLL times so two
+    // dependent chains interleave): one copy of its code per stage instead of C (fully unrolled it was 19 456
+    // instructions for largey/RK45/C=8 and 30 % of the stall samples were instruction fetch; as one call per component
+    // it paid its literals and ~25 marshalling instructions per component, profiles/r01_notes.md), loop-invariant
+    // work (constants, anything that depends on t only) hoisted by the compiler.  A rolled loop cannot index a register
+    // array, so the values go to the thread's own slots of a shared-memory vector: K_J's own vector when K_J lives in
+    // memory, else `stg` -- the vector of the first memory-resident K (dead while a register-resident K_J, J < NREG, is
+    // computed: stages run in order and every K_j, j >= 1, dies with the attempt) or a vector of its own -- and are
+    // read back with immediate offsets.  Own slots only: no barrier.
+    // A problem may split its functor into tprep(t, args) -- whatever depends on t and args only, computed once per
+    // evaluation and thread -- and eval_u(i, u, ..., slow) (ProbLargeY: the phase 2*pi*t/5).  eval_u has no slow path of
+    // its own (a branch per component would keep the unrolled chains from interleaving): it raises `slow` when an
+    // argument left the range of its fast arithmetic, and the thread then redoes its components with eval().
+    // Slots past n_y (the CTA's padding) evaluate component n_y - 1: no branch, and nobody reads those slots.
+    CYRK_DI void eval_into(double* dst, double t, const double* in) const
     {
-        return Prob::eval(i, t, in, n, args, aux);
-    }
-    CYRK_DI static double eval_one(unsigned i, double t, const double* in, unsigned n, const char* args, const double* aux)
-    {
-        if constexpr (Prob::INLINE_EVAL) return Prob::eval(i, t, in, n, args, aux);
-        else return eval_call(i, t, in, n, args, aux);
-    }
-
-    // Several components per call (CYRK_EVAL_GROUP, a divisor of C): the callee's constants and the call marshalling
-    // are paid once per group, and the group's dependent chains (range reduction -> polynomial) interleave.  The
-    // struct comes back in registers (checked in SASS: no local memory).
-    template <int W> struct EvalGroup { double v[W]; };
-    template <int W>
-    static __device__ __noinline__ EvalGroup<W> eval_group_call(unsigned i0, unsigned stride, double t, const double* in, unsigned n,
-                                                                const char* args, const double* aux)
-    {
-        EvalGroup<W> r;
-#pragma unroll
-        for (int w = 0; w < W; w++) {
-            const unsigned i = i0 + (unsigned)w * stride;
-            r.v[w] = i < n ? Prob::eval(i, t, in, n, args, aux) : 0.0;
+        constexpr int UNR = CYRK_EVAL_UNROLL < C ? CYRK_EVAL_UNROLL : C;
+        const unsigned last = n - 1u;
+        if constexpr (HasTprep<Prob>::value) {
+            auto u = Prob::tprep(t, args);
+            asm volatile("" : "+d"(u));             // opaque: not recomputed inside the loop
+            unsigned slow = 0u;
+#pragma unroll(UNR)
+            for (int c = 0; c < C; c++) {
+                const unsigned i = comp(c);
+                dst[i] = Prob::eval_u(i < last ? i : last, u, in, n, args, aux(), slow);
+            }
+            if (Prob::is_slow(slow)) {
+#pragma unroll 1
+                for (int c = 0; c < C; c++) {
+                    const unsigned i = comp(c);
+                    dst[i] = Prob::eval(i < last ? i : last, t, in, n, args, aux());
+                }
+            }
+        } else {
+#pragma unroll(UNR)
+            for (int c = 0; c < C; c++) {
+                const unsigned i = comp(c);
+                dst[i] = Prob::eval(i < last ? i : last, t, in, n, args, aux());
+            }
         }
-        return r;
     }
-
-    // K_J = f(t, in) for the components this thread owns; `in` must be complete (the caller has synchronised)
     template <int J>
     CYRK_DI void eval_rhs(double t, const double* in)
     {
-        constexpr int W = CYRK_EVAL_GROUP;
-        if constexpr (!Prob::INLINE_EVAL && W > 1 && C % W == 0) {
-#pragma unroll
-            for (int c0 = 0; c0 < C; c0 += W) {
-                const EvalGroup<W> g = eval_group_call<W>(comp(c0), T, t, in, n, args, aux);
-#pragma unroll
-                for (int w = 0; w < W; w++) kset<J>(c0 + w, g.v[w]);
-            }
-        } else {
+        if constexpr (Prob::INLINE_EVAL) {           // a handful of instructions: straight into K_J
 #pragma unroll
             for (int c = 0; c < C; c++) {
                 const unsigned i = comp(c);
-                kset<J>(c, i < n ? eval_one(i, t, in, n, args, aux) : 0.0);
+                kset<J>(c, i < n ? Prob::eval(i, t, in, n, args, aux()) : 0.0);
             }
+        } else if constexpr (J < NREG) {
+            eval_into(stg(), t, in);
+#pragma unroll
+            for (int c = 0; c < C; c++) kr[J][c] = stg()[comp(c)];
+        } else {
+            eval_into(kvec<J>(), t, in);
         }
         nfev++;
     }
@@ -192,8 +219,8 @@ struct Cta2Solver {
     CYRK_DI void compute_stages()
     {
         // never start in the buffer that holds y_now (it is still read below); then alternate
-        double* in = (ybuf == buf0) ? buf1 : buf0;
-        double* other = (ybuf == buf0) ? buf0 : buf1;
+        int ib = yb ^ 1;
+        double* in = buf(ib);
         {
             const double a10 = Ld::a(1, 0);
 #pragma unroll
@@ -204,7 +231,7 @@ struct Cta2Solver {
             }
             __syncthreads();
             eval_rhs<1>(t_old + Ld::c(1) * step, in);
-            double* t = in; in = other; other = t;
+            ib ^= 1; in = buf(ib);
         }
         static_for<2, NS>([&](auto ss) {
             constexpr int S = decltype(ss)::value;
@@ -212,14 +239,14 @@ struct Cta2Solver {
             for (int c = 0; c < C; c++) in[comp(c)] = yo[c] + (step * dot_k<ARow<S>, S>(c, ARow<S>{}));
             __syncthreads();
             eval_rhs<S>(t_old + Ld::c(S) * step, in);
-            double* t = in; in = other; other = t;
+            ib ^= 1; in = buf(ib);
         });
 #pragma unroll
         for (int c = 0; c < C; c++) in[comp(c)] = yo[c] + (step * dot_k<BRow, NS>(c, BRow{}));
         __syncthreads();
         eval_rhs<NS>(t_now, in);
-        ybuf = in;
-        ystep = in;
+        yb = ib;
+        ys = ib;
     }
 
     // rk.cpp:778-823, 1027-1075, 1414-1489.  Strict build: returns err (reference formulas).  Production build:
@@ -233,7 +260,7 @@ struct Cta2Solver {
                 const unsigned i = comp(c);
                 if (i < n) {
                     const double e = dot_k<ERow, NK>(c, ERow{});
-                    const double yn = ybuf[i];
+                    const double yn = ybuf()[i];
 #if CYRK_FP_STRICT
                     const double sc = e / (atol_at(p, i) + fmax(fabs(yo[c]), fabs(yn)) * rtol_at(p, i));
                     part += (sc * sc);
@@ -255,7 +282,7 @@ struct Cta2Solver {
             for (int c = 0; c < C; c++) {
                 const unsigned i = comp(c);
                 if (i < n) {
-                    const double yn = ybuf[i];
+                    const double yn = ybuf()[i];
 #if CYRK_FP_STRICT
                     const double scale_inv = 1.0 / (atol_at(p, i) + fmax(fabs(yo[c]), fabs(yn)) * rtol_at(p, i));
 #else
@@ -301,16 +328,19 @@ struct Cta2Solver {
         if (!((d0 < 1.0e-5) || (d1 < 1.0e-5))) h0 = 0.01 * d0 / d1;
         const double h0_dir = fwd ? h0 : -h0;
         t_now = t_old + h0_dir;
-        double* in = buf1;                        // buf0 keeps y0 == y_now
+        double* in = buf(1);                      // buffer 0 keeps y0 == y_now
 #pragma unroll
         for (int c = 0; c < C; c++) in[comp(c)] = yo[c] + h0_dir * kget<0>(c);
         __syncthreads();
         double cc = 0.0;
+        if constexpr (!Prob::INLINE_EVAL) eval_into(stg(), t_now, in);      // every K_j, j >= 1, is dead here
 #pragma unroll
         for (int c = 0; c < C; c++) {
             const unsigned i = comp(c);
             if (i < n) {
-                const double f1 = eval_one(i, t_now, in, n, args, aux);
+                double f1;
+                if constexpr (Prob::INLINE_EVAL) f1 = Prob::eval(i, t_now, in, n, args, aux());
+                else f1 = stg()[i];
                 const double scale = atol_at(p, i) + fabs(yo[c]) * rtol_at(p, i);
                 const double a2 = (f1 - kget<0>(c)) / scale;
                 cc += (a2 * a2);
@@ -342,7 +372,7 @@ struct Cta2Solver {
             const double q1 = h * dot_k<DRow<2>, 16>(c, DRow<2>{});
             const double q2 = h * dot_k<DRow<1>, 16>(c, DRow<1>{});
             const double q3 = h * dot_k<DRow<0>, 16>(c, DRow<0>{});
-            const double delta_y = (EVENTS ? ystep : ybuf)[comp(c)] - yo[c];
+            const double delta_y = (EVENTS ? ystep() : ybuf())[comp(c)] - yo[c];
             const double sum_dy = kget<NS>(c) + kget<0>(c);
             const double q4 = 2.0 * delta_y - h * sum_dy;
             const double q5 = h * kget<0>(c) - delta_y;
@@ -364,7 +394,7 @@ struct Cta2Solver {
     CYRK_DI void dense_extra_stages()
     {
         if constexpr (Tab::IS_DOP) {
-            double* in = (ybuf == buf0) ? buf1 : buf0;
+            double* in = buf(yb ^ 1);
 #pragma unroll
             for (int c = 0; c < C; c++) in[comp(c)] = yo[c] + dot_k<XRow<0>, 13>(c, XRow<0>{}) * step;
             __syncthreads();
@@ -392,14 +422,14 @@ struct Cta2Solver {
             if (tid == 0) p.t_rows[r] = t;
             double* dst = p.y_rows + r * ndy;
 #pragma unroll
-            for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) dst[i] = ybuf[i]; }
+            for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) dst[i] = ybuf()[i]; }
         }
         if constexpr (Prob::HAS_EXTRAS) {
             // extra outputs of this row = components n.. of the functor at (t, y): what the right-hand-side call that
             // produced dy_now wrote to dy[n_y:] (same inputs -> same values).  ybuf is complete and visible here: the last
             // stage evaluation read it after a barrier.  (No t_eval / events / dense store with extras on this path.)
             for (unsigned j = tid; j < p.n_extra; j += T) {
-                const double v = Prob::eval(n + j, t, ybuf, n, args, aux);
+                const double v = Prob::eval(n + j, t, ybuf(), n, args, aux());
                 if (row) p.y_rows[(traj * p.row_cap + size) * ndy + n + j] = v;
                 p.y_last[traj * ndy + n + j] = v;
             }
@@ -410,7 +440,7 @@ struct Cta2Solver {
             // (without t_eval the final write-out stores it once)
             double* yl = p.y_last + traj * ndy;
 #pragma unroll
-            for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) yl[i] = ybuf[i]; }
+            for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) yl[i] = ybuf()[i]; }
         }
         t_last = t;
         size++;
@@ -445,7 +475,7 @@ struct Cta2Solver {
                         q[1] = step * dot_k<DRow<2>, 16>(c, DRow<2>{});
                         q[2] = step * dot_k<DRow<1>, 16>(c, DRow<1>{});
                         q[3] = step * dot_k<DRow<0>, 16>(c, DRow<0>{});
-                        const double delta_y = (EVENTS ? ystep : ybuf)[i] - yo[c];
+                        const double delta_y = (EVENTS ? ystep() : ybuf())[i] - yo[c];
                         const double sum_dy = kget<NS>(c) + kget<0>(c);
                         q[4] = 2.0 * delta_y - step * sum_dy;
                         q[5] = step * kget<0>(c) - delta_y;
@@ -545,20 +575,20 @@ struct Cta2Solver {
         t_last = d_nan();
         inv_n = 1.0 / (double)n;
         const double* y0 = p.y0 + traj * n;
-        ybuf = buf0;
-        ystep = buf0;
+        yb = 0;
+        ys = 0;
         __syncthreads();                                   // the previous trajectory's readers are done with the buffers
 #pragma unroll
         for (int c = 0; c < C; c++) {
             const unsigned i = comp(c);
             const double v = i < n ? y0[i] : 0.0;
             yo[c] = v;
-            ybuf[i] = v;
+            buf(0)[i] = v;
         }
-        Prob::prepare(args, n, aux, prepared && p.args_stride == 0);   // cooperative; ends with __syncthreads()
+        Prob::prepare(args, n, aux(), prepared && p.args_stride == 0);   // cooperative; ends with __syncthreads()
         prepared = true;
         __syncthreads();
-        eval_rhs<0>(t_now, ybuf);                          // RHS evaluation #1
+        eval_rhs<0>(t_now, ybuf());                         // RHS evaluation #1
         if (p.n_t_eval == 0) save_row_from_ybuf(p, traj, t_now);
         te_old = fwd ? 0u : p.n_t_eval;
         // per-event state, replicated in every thread (all copies evolve identically)
@@ -570,7 +600,7 @@ struct Cta2Solver {
         int term_index = -1;
         if constexpr (EVENTS) {
             if (tid == 0)
-                for (int e = 0; e < p.n_events; e++) gsh[1 + e] = Prob::event(p.ev_id[e], t_now, ybuf, n, args);
+                for (int e = 0; e < p.n_events; e++) gsh[1 + e] = Prob::event(p.ev_id[e], t_now, ybuf(), n, args);
             __syncthreads();
             for (int e = 0; e < p.n_events; e++) { g_old[e] = gsh[1 + e]; ev_seen[e] = 0; ev_hits[e] = 0; ev_root[e] = 0.0; }
         }
@@ -647,7 +677,7 @@ struct Cta2Solver {
             bool extra_counted = false;
             if constexpr (EVENTS) {                        // p_check_events, cysolver.cpp:563-750
                 if (tid == 0)
-                    for (int e = 0; e < p.n_events; e++) gsh[1 + e] = Prob::event(p.ev_id[e], t_now, ybuf, n, args);
+                    for (int e = 0; e < p.n_events; e++) gsh[1 + e] = Prob::event(p.ev_id[e], t_now, ybuf(), n, args);
                 __syncthreads();
                 unsigned mask = 0;
                 for (int e = 0; e < p.n_events; e++) {
@@ -668,7 +698,8 @@ struct Cta2Solver {
                     }
                 }
                 if (mask != 0u) {
-                    double* scr = (ybuf == buf0) ? buf1 : buf0;
+                    const int scr_b = yb ^ 1;
+                    double* scr = buf(scr_b);
                     double term_root = fwd ? d_inf() : -d_inf();
                     for (int e = 0; e < p.n_events && !error_flag; e++) {
                         if (!(mask & (1u << e))) continue;
@@ -708,7 +739,7 @@ struct Cta2Solver {
                                 __syncthreads();               // thread 0 may still be reading scr
                                 t_now = term_root;
                                 interp_into(scr, t_now, t_step_old, h_step);
-                                ybuf = scr;
+                                yb = scr_b;
                             }
                         }
                     }
@@ -761,13 +792,13 @@ struct Cta2Solver {
             // roll: y_old <- y_now, K_0 <- K_NS (FSAL); own components only, no barrier needed
             t_old = t_now;
 #pragma unroll
-            for (int c = 0; c < C; c++) { yo[c] = ybuf[comp(c)]; kset<0>(c, kget<NS>(c)); }
+            for (int c = 0; c < C; c++) { yo[c] = ybuf()[comp(c)]; kset<0>(c, kget<NS>(c)); }
         }
         // ---- results
         if (p.n_t_eval == 0) {
             double* yl = p.y_last + traj * (Prob::HAS_EXTRAS ? n + p.n_extra : n);   // (the extras of the last saved row are already there)
 #pragma unroll
-            for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) yl[i] = ybuf[i]; }
+            for (int c = 0; c < C; c++) { const unsigned i = comp(c); if (i < n) yl[i] = ybuf()[i]; }
         } else if (size == 0) {
             double* yl = p.y_last + traj * n;
 #pragma unroll
@@ -806,10 +837,7 @@ CYRK_DI void rk_cta2_body(const CtaParams& p)
     S.red = red;
     S.red_phase = 0;
     S.prepared = false;
-    S.buf0 = smem;
-    S.buf1 = smem + S.V;
-    S.aux = smem + 2u * S.V;
-    S.ksm = smem + 3u * S.V;
+    S.sm = smem;
     // per-CTA global slab: the K vectors that fit neither registers nor shared memory, then one vector for root searches
     S.kgl = p.scratch + (unsigned long long)blockIdx.x * (unsigned long long)((Solver::NGL > 0 ? Solver::NGL : 1) + 1) * S.V;
     S.xbuf = S.kgl + (unsigned long long)(Solver::NGL > 0 ? Solver::NGL : 1) * S.V;
@@ -827,7 +855,7 @@ CYRK_DI void rk_cta2_body(const CtaParams& p)
 }
 
 template <class Prob, int METHOD, int C, bool EVENTS>
-__global__ void __launch_bounds__(cta2_max_block, 1) rk_cta2_kernel(const __grid_constant__ CtaParams p)
+__global__ void __launch_bounds__(cta2_threads(C), 1) rk_cta2_kernel(const __grid_constant__ CtaParams p)
 {
     rk_cta2_body<Prob, METHOD, C, EVENTS>(p);
 }

@@ -75,15 +75,25 @@ struct CtaDenseEvalParams {
 
 // ---- register-resident kernel (cta2_core.cuh): compile-time placement of the stage derivatives K_0..K_{nkd-1}
 // for C components per thread.  Shared by the kernel and the host launcher.
+// C components per thread, C in {1, 2, 4, 8, 16}.  C <= 8: 512 threads (128 registers each, one CTA per SM at full size);
+// C = 16: 256 threads with up to 255 registers -- the per-thread scalars (step-size controller, addresses, loop
+// overhead) are paid by half as many threads and no longer compete with the state for registers.
 constexpr int cta2_max_block = 512;
-constexpr int cta2_reg_doubles(int C) { return C >= 8 ? 32 : 40; }            // y_old + NREG derivative vectors per thread
+constexpr int cta2_max_components = 4096;
+constexpr int cta2_threads(int C) { return C >= 16 ? 256 : cta2_max_block; }
+constexpr int cta2_reg_doubles(int C) { return C >= 16 ? 64 : C >= 8 ? 32 : 40; }   // y_old + NREG derivative vectors per thread
 constexpr int cta2_nkd(int method) { return method == 3 ? 4 : method == 4 ? 7 : 16; }      // RK23 / RK45 / DOP853 (+3 dense)
 constexpr int cta2_nreg(int nkd, int C) { return (cta2_reg_doubles(C) / C - 1) < nkd ? (cta2_reg_doubles(C) / C - 1) : nkd; }
-constexpr int cta2_sm_slots(int C) { return (227 * 1024 - 1024) / (C * cta2_max_block * 8); }
+constexpr int cta2_sm_slots(int C) { return (227 * 1024 - 1024) / (C * cta2_threads(C) * 8); }
 constexpr int cta2_nsm(int nkd, int C)
 {
     return (nkd - cta2_nreg(nkd, C)) < (cta2_sm_slots(C) - 3) ? (nkd - cta2_nreg(nkd, C)) : (cta2_sm_slots(C) - 3);
 }
 constexpr int cta2_ngl(int nkd, int C) { return nkd - cta2_nreg(nkd, C) - cta2_nsm(nkd, C); }
+// shared-memory vectors of the kernel: two stage-input buffers, the aux table, the memory-resident derivatives, and a
+// staging vector for right-hand-side evaluations when no derivative lives in shared memory (else K_NREG's doubles as it)
+constexpr int cta2_smem_vectors(int nkd, int C) { return 3 + cta2_nsm(nkd, C) + (cta2_nsm(nkd, C) > 0 ? 0 : 1); }
+// threads per CTA: with C >= 2 always cta2_threads(C) (compile-time component stride), with C == 1 one per component
+constexpr int cta2_block(unsigned long long n, int C) { return C >= 2 ? cta2_threads(C) : (int)((n + 31) / 32 * 32); }
 
 }  // namespace cyrk

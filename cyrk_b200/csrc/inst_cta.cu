@@ -52,6 +52,9 @@ cudaError_t by_c(int C, const CtaParams& p, int grid, int block, size_t smem, cu
     case 2: return go2<Prob, METHOD, 2>(p, grid, block, smem, s);
     case 4: return go2<Prob, METHOD, 4>(p, grid, block, smem, s);
     case 8: return go2<Prob, METHOD, 8>(p, grid, block, smem, s);
+    case 16:                        // 256 threads x 16 components (RK23 / RK45; DOP853's 16 stage vectors would live in L2)
+        if constexpr (METHOD != METHOD_DOP853) return go2<Prob, METHOD, 16>(p, grid, block, smem, s);
+        else return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
     }
 }

@@ -1,11 +1,8 @@
 #!/bin/bash
-P=${1:-r02_s9}
+P=${1:-r02_s14}
 O=gpurun_out
 mkdir -p $O
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/${P}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/${P}_smoke.log
-timeout 1800 python -m pytest tests -m gpu -q -x > $O/${P}_gpu_tests.log 2>&1
-tail -3 $O/${P}_gpu_tests.log
-timeout 600 python scripts/bench_c4.py > $O/${P}_c4.log 2>&1; tail -6 $O/${P}_c4.log
-timeout 1200 python bench.py > $O/${P}_bench.json 2> $O/${P}_bench.err
-echo "bench rc=$?"
+python scripts/quick_c4.py > $O/${P}_c4.log 2>&1; cat $O/${P}_c4.log
+timeout 1800 python -m pytest tests/test_gpu_largey.py tests/test_user_rhs.py tests/test_gpu_math.py -m gpu -q -x > $O/${P}_gpu_tests.log 2>&1
+tail -5 $O/${P}_gpu_tests.log
 echo done
