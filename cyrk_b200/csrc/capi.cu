@@ -87,7 +87,7 @@ void registry_init()
 static int g_opt_refill_min = 0;      // 0 = automatic (1 with prep, 4 without)
 static int g_opt_prep = -1;           // -1 = automatic (n_traj >= 2 Mi), 1 = always, 0 = never
 static int g_opt_block = 0;            // threads per CTA of the thread-per-trajectory kernels; 0 = pick by occupancy (128 or 96)
-static int g_opt_cta2_wide = 1;       // register-resident CTA kernel above 2048 components: 16 per thread x 256 threads
+static int g_opt_cta2_large = 1;      // register-resident CTA kernel for 4096 < n_y <= 12 288 (derivatives in the L2 slab); 0: cta_core.cuh
 static int g_opt_cta_smem_vecs = -1;  // CTA path: working vectors kept in shared memory (-1 = as many as fit)
 static int g_opt_cta_block = 0;       // CTA path: threads per CTA (0 = by n_y)
 static int g_opt_pipe_taper = 1;       // pipelined host-I/O path: short first / last chunks
@@ -1537,7 +1537,12 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     const bool dop_c8 = a.method == CYRK_METHOD_DOP853 && N > (size_t)4 * cta2_max_block && !a.dense_output && a.n_events == 0;
     bool whole_vector = false;           // user system in the whole-vector form: one thread evaluates it (slab kernel only)
     if (user_rhs) { int uny = 0, unx = 0, una = 0, une = 0; if (user_rhs_info(a.rhs_id, &uny, &unx, &una, &une) == 0) whole_vector = uny > CYRK_MAX_NY; }
-    const bool use_cta2 = !whole_vector && g_opt_cta_kernel != 1 && N <= (size_t)8 * cta2_max_block && !(dop_c8 && g_opt_cta_kernel == 0);
+    // n_y in (4096, 12 288]: the same kernel with the stage derivatives in the L2-resident slab (RK23 / RK45, no events,
+    // no stored dense output); beyond that, and for DOP853, the shared-memory/slab kernel of cta_core.cuh
+    const bool cta2_slab_ok = N > (size_t)cta2_max_c_onchip * cta2_max_block && N <= (size_t)cta2_max_c * cta2_max_block &&
+                              a.method != CYRK_METHOD_DOP853 && a.n_events == 0 && !dense && g_opt_cta2_large;
+    const bool use_cta2 = !whole_vector && g_opt_cta_kernel != 1 &&
+                          ((N <= (size_t)cta2_max_c_onchip * cta2_max_block && !(dop_c8 && g_opt_cta_kernel == 0)) || cta2_slab_ok);
     int cta2_C = 0;
     int block, grid;
     size_t smem;
@@ -1563,21 +1568,18 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         return -1;
     }
     if (use_cta2) {
-        cta2_C = N <= (size_t)cta2_max_block ? 1 : N <= (size_t)2 * cta2_max_block ? 2 : N <= (size_t)4 * cta2_max_block ? 4 : 8;
-        // above 2048 components: 256 threads x 16 components instead of 512 x 8 (cta_core_params.h); built-in RK23 / RK45
-        if (cta2_C == 8 && g_opt_cta2_wide && a.method != CYRK_METHOD_DOP853 && !user_rhs) cta2_C = 16;
+        cta2_C = cta2_choose_c(N);
         block = cta2_block(N, cta2_C);
         const size_t V = (size_t)block * cta2_C;
         const int nkd = cta2_nkd(a.method);
         smem = (size_t)cta2_smem_vectors(nkd, cta2_C) * V * 8;
         if (smem + 1024 > (size_t)optin) { set_error("internal: CTA kernel shared-memory layout exceeds the device limit"); return -1; }
         // registers: the kernel is compiled for <= 128 per thread (__launch_bounds__(512, 1))
-        const size_t by_regs = std::max<size_t>(1, (size_t)65536 / ((size_t)(cta2_C >= 16 ? 255 : 128) * block));
+        const size_t by_regs = std::max<size_t>(1, (size_t)65536 / ((size_t)128 * block));
         const size_t by_smem = std::max<size_t>(1, (size_t)smem_per_sm / (smem + 2048));
         const int per_sm = (int)std::min<size_t>({(size_t)8, by_regs, by_smem});
         grid = (int)std::min<unsigned long long>((unsigned long long)device_sm_count(h->device) * per_sm, B);
-        const size_t ngl = (size_t)std::max(1, cta2_ngl(nkd, cta2_C)) + 1;      // + one vector for event root searches
-        if (h->d_scratch.ensure((size_t)grid * ngl * V * 8)) return -1;
+        if (h->d_scratch.ensure((size_t)grid * (size_t)cta2_slab_vectors(nkd, cta2_C) * V * 8)) return -1;
         p.scratch = h->d_scratch.as<double>();
     } else {
         // launch geometry: one CTA per SM when the working set fills shared memory, more when it is small
@@ -2241,7 +2243,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "events_two_pass")) { g_opt_events_two_pass = value; return 0; }
     if (!strcmp(name, "events_static")) { g_opt_events_static = value; return 0; }
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
-    if (!strcmp(name, "cta2_wide")) { g_opt_cta2_wide = value; return 0; }
+    if (!strcmp(name, "cta2_large")) { g_opt_cta2_large = value; return 0; }
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
     if (!strcmp(name, "cta_kernel")) { g_opt_cta_kernel = value; return 0; }
     if (!strcmp(name, "pipe_taper")) { g_opt_pipe_taper = value; return 0; }

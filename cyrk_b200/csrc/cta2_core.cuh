@@ -27,8 +27,11 @@
 // this path (the host shim rejects it): extra outputs.
 #pragma once
 
+#ifndef CYRK_EVAL_WIDTH
+#define CYRK_EVAL_WIDTH 2      // components per call of a problem's phase-interleaved evaluation (eval_uw), where it has one
+#endif
 #ifndef CYRK_EVAL_UNROLL
-#define CYRK_EVAL_UNROLL 4     // unroll factor of the per-thread component loop of a right-hand-side evaluation
+#define CYRK_EVAL_UNROLL 8     // unroll factor of the per-thread component loop of a right-hand-side evaluation
 #endif
 #include "rk_core.cuh"
 #include "cta_core_params.h"
@@ -90,9 +93,24 @@ struct Cta2Solver {
     CYRK_DI double* buf(int b) const { return sm + (b ? vlen() : 0u); }
     CYRK_DI double* ybuf() const { return buf(yb); }
     CYRK_DI const double* ystep() const { return buf(ys); }
-    CYRK_DI double* aux() const { return sm + 2u * vlen(); }
+    static constexpr bool AUX_GLOBAL = cta2_aux_global(C);
+    static constexpr int NGL_ALLOC = NGL > 0 ? NGL : 1;
+    static constexpr int SLAB_VECTORS = cta2_slab_vectors(NKD, C);
+    CYRK_DI double* aux() const
+    {
+        if constexpr (AUX_GLOBAL) return kgl + (unsigned long long)(NGL_ALLOC + 1) * vlen();
+        else return sm + 2u * vlen();
+    }
     CYRK_DI double* ksm() const { return sm + 3u * vlen(); }
-    CYRK_DI double* stg() const { return sm + 3u * vlen(); }      // staging vector of eval_rhs: K_NREG's, or its own when NSM == 0
+    // Staging vector of eval_rhs (and of first_step_size's trial evaluation): the vector of the first memory-resident
+    // K_j with j >= 1 -- dead whenever a register-resident K_J, J < j, or the trial derivative is computed -- or a
+    // vector of its own when every K is in registers.
+    static constexpr int STG_J = NREG > 1 ? NREG : 1;
+    CYRK_DI double* stg() const
+    {
+        if constexpr (STG_J >= NKD) return sm + 3u * vlen();
+        else return kvec<STG_J>();
+    }
     template <int J> CYRK_DI double* kvec() const        // where K_J lives when it is not in registers
     {
         static_assert(J >= NREG, "K_J is register-resident");
@@ -176,10 +194,25 @@ struct Cta2Solver {
             auto u = Prob::tprep(t, args);
             asm volatile("" : "+d"(u));             // opaque: not recomputed inside the loop
             unsigned slow = 0u;
+            constexpr int W = CYRK_EVAL_WIDTH < C ? CYRK_EVAL_WIDTH : C;
+            if constexpr (W > 1 && C % W == 0) {
+                constexpr int UNG = (UNR / W) > 0 ? (UNR / W) : 1;
+#pragma unroll(UNG)
+                for (int c0 = 0; c0 < C; c0 += W) {
+                    unsigned ii[W];
+                    double out[W];
+#pragma unroll
+                    for (int w = 0; w < W; w++) { const unsigned i = comp(c0 + w); ii[w] = i < last ? i : last; }
+                    Prob::template eval_uw<W>(ii, u, in, n, args, aux(), slow, out);
+#pragma unroll
+                    for (int w = 0; w < W; w++) dst[comp(c0 + w)] = out[w];
+                }
+            } else {
 #pragma unroll(UNR)
-            for (int c = 0; c < C; c++) {
-                const unsigned i = comp(c);
-                dst[i] = Prob::eval_u(i < last ? i : last, u, in, n, args, aux(), slow);
+                for (int c = 0; c < C; c++) {
+                    const unsigned i = comp(c);
+                    dst[i] = Prob::eval_u(i < last ? i : last, u, in, n, args, aux(), slow);
+                }
             }
             if (Prob::is_slow(slow)) {
 #pragma unroll 1
@@ -839,8 +872,8 @@ CYRK_DI void rk_cta2_body(const CtaParams& p)
     S.prepared = false;
     S.sm = smem;
     // per-CTA global slab: the K vectors that fit neither registers nor shared memory, then one vector for root searches
-    S.kgl = p.scratch + (unsigned long long)blockIdx.x * (unsigned long long)((Solver::NGL > 0 ? Solver::NGL : 1) + 1) * S.V;
-    S.xbuf = S.kgl + (unsigned long long)(Solver::NGL > 0 ? Solver::NGL : 1) * S.V;
+    S.kgl = p.scratch + (unsigned long long)blockIdx.x * (unsigned long long)Solver::SLAB_VECTORS * S.V;
+    S.xbuf = S.kgl + (unsigned long long)Solver::NGL_ALLOC * S.V;
     S.uni_tol = p.uniform_tol != 0;
     S.rt0 = p.rtol0;
     S.at0 = p.atol0;

@@ -75,24 +75,41 @@ struct CtaDenseEvalParams {
 
 // ---- register-resident kernel (cta2_core.cuh): compile-time placement of the stage derivatives K_0..K_{nkd-1}
 // for C components per thread.  Shared by the kernel and the host launcher.
-// C components per thread, C in {1, 2, 4, 8, 16}.  C <= 8: 512 threads (128 registers each, one CTA per SM at full size);
-// C = 16: 256 threads with up to 255 registers -- the per-thread scalars (step-size controller, addresses, loop
-// overhead) are paid by half as many threads and no longer compete with the state for registers.
+// C components per thread, 512 threads (C = 1: one thread per component).  C in {1, 2, 4, 8}: n_y <= 4096, every vector
+// on chip (registers + shared memory; DOP853 at C = 8 puts nine of its 16 stage vectors into the L2-resident slab).
+// C in {12, 16, 20, 24}: n_y <= 12 288 (the reference's largey has 10 000): the two stage-input buffers stay in shared
+// memory, y_old (and K_0 while it fits) in registers, the other stage derivatives -- and from C = 20 the problem's aux
+// table -- in the per-CTA slab of global memory, which stays L2-resident (148 CTAs x <= 9 vectors x <= 96 KB << 126 MB).
 constexpr int cta2_max_block = 512;
-constexpr int cta2_max_components = 4096;
-constexpr int cta2_threads(int C) { return C >= 16 ? 256 : cta2_max_block; }
-constexpr int cta2_reg_doubles(int C) { return C >= 16 ? 64 : C >= 8 ? 32 : 40; }   // y_old + NREG derivative vectors per thread
+constexpr int cta2_max_c_onchip = 8;
+constexpr int cta2_max_c = 24;
+constexpr int cta2_threads(int) { return cta2_max_block; }
+constexpr int cta2_choose_c(unsigned long long n)
+{
+    return n <= 512 ? 1 : n <= 1024 ? 2 : n <= 2048 ? 4 : n <= 4096 ? 8 : n <= 6144 ? 12 : n <= 8192 ? 16 : n <= 10240 ? 20 : n <= 12288 ? 24 : 0;
+}
+// doubles of state per thread kept in registers: y_old + NREG derivative vectors
+constexpr int cta2_reg_doubles(int C) { return C >= 20 ? C : C >= 12 ? 2 * C : C >= 8 ? 32 : 40; }
 constexpr int cta2_nkd(int method) { return method == 3 ? 4 : method == 4 ? 7 : 16; }      // RK23 / RK45 / DOP853 (+3 dense)
 constexpr int cta2_nreg(int nkd, int C) { return (cta2_reg_doubles(C) / C - 1) < nkd ? (cta2_reg_doubles(C) / C - 1) : nkd; }
 constexpr int cta2_sm_slots(int C) { return (227 * 1024 - 1024) / (C * cta2_threads(C) * 8); }
+// shared memory: [stage-input buffer 0 | buffer 1 | aux (when a third vector fits) | NSM derivative vectors]
+constexpr bool cta2_aux_global(int C) { return cta2_sm_slots(C) < 3; }
 constexpr int cta2_nsm(int nkd, int C)
 {
-    return (nkd - cta2_nreg(nkd, C)) < (cta2_sm_slots(C) - 3) ? (nkd - cta2_nreg(nkd, C)) : (cta2_sm_slots(C) - 3);
+    return cta2_sm_slots(C) <= 3 ? 0
+         : (nkd - cta2_nreg(nkd, C)) < (cta2_sm_slots(C) - 3) ? (nkd - cta2_nreg(nkd, C)) : (cta2_sm_slots(C) - 3);
 }
 constexpr int cta2_ngl(int nkd, int C) { return nkd - cta2_nreg(nkd, C) - cta2_nsm(nkd, C); }
-// shared-memory vectors of the kernel: two stage-input buffers, the aux table, the memory-resident derivatives, and a
-// staging vector for right-hand-side evaluations when no derivative lives in shared memory (else K_NREG's doubles as it)
-constexpr int cta2_smem_vectors(int nkd, int C) { return 3 + cta2_nsm(nkd, C) + (cta2_nsm(nkd, C) > 0 ? 0 : 1); }
+// The staging vector of a right-hand-side evaluation whose K_J is register-resident is the vector of the first
+// memory-resident K_j, j >= 1 (shared memory or slab; dead at that point); only when every derivative (from K_1 on) is
+// in registers does the kernel need one more shared-memory vector.
+constexpr int cta2_smem_vectors(int nkd, int C)
+{
+    return (cta2_aux_global(C) ? 2 : 3) + cta2_nsm(nkd, C) + ((cta2_nreg(nkd, C) > 1 ? cta2_nreg(nkd, C) : 1) >= nkd ? 1 : 0);
+}
+// per-CTA slab of global memory, in vectors: [max(NGL, 1) derivatives | one vector for event root searches | aux if not in smem]
+constexpr int cta2_slab_vectors(int nkd, int C) { return (cta2_ngl(nkd, C) > 0 ? cta2_ngl(nkd, C) : 1) + 1 + (cta2_aux_global(C) ? 1 : 0); }
 // threads per CTA: with C >= 2 always cta2_threads(C) (compile-time component stride), with C == 1 one per component
 constexpr int cta2_block(unsigned long long n, int C) { return C >= 2 ? cta2_threads(C) : (int)((n + 31) / 32 * 32); }
 

@@ -52,9 +52,12 @@ cudaError_t by_c(int C, const CtaParams& p, int grid, int block, size_t smem, cu
     case 2: return go2<Prob, METHOD, 2>(p, grid, block, smem, s);
     case 4: return go2<Prob, METHOD, 4>(p, grid, block, smem, s);
     case 8: return go2<Prob, METHOD, 8>(p, grid, block, smem, s);
-    case 16:                        // 256 threads x 16 components (RK23 / RK45; DOP853's 16 stage vectors would live in L2)
-        if constexpr (METHOD != METHOD_DOP853) return go2<Prob, METHOD, 16>(p, grid, block, smem, s);
-        else return cudaErrorInvalidValue;
+    // n_y in (4096, 12 288]: derivatives in the L2-resident slab; RK23 / RK45 without events (DOP853's 16 vectors of
+    // 96 KB x 148 CTAs would not stay in L2; cta_core.cuh takes it)
+    case 12: if constexpr (METHOD != METHOD_DOP853) return go2e<Prob, METHOD, 12, false>(p, grid, block, smem, s); else return cudaErrorInvalidValue;
+    case 16: if constexpr (METHOD != METHOD_DOP853) return go2e<Prob, METHOD, 16, false>(p, grid, block, smem, s); else return cudaErrorInvalidValue;
+    case 20: if constexpr (METHOD != METHOD_DOP853) return go2e<Prob, METHOD, 20, false>(p, grid, block, smem, s); else return cudaErrorInvalidValue;
+    case 24: if constexpr (METHOD != METHOD_DOP853) return go2e<Prob, METHOD, 24, false>(p, grid, block, smem, s); else return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
     }
 }

@@ -41,6 +41,49 @@ struct ProbLargeY {
         return aux[i] * y[i] * CYRK_FP_NS::psin_pi(x);
     }
     __device__ __forceinline__ static bool is_slow(unsigned slow) { return slow >= 0x40F86A00u; }
+    // W components at once, written phase by phase so that the W dependent chains (reduction -> polynomial) are issued
+    // interleaved: with four warps per scheduler one chain per warp leaves the FP64 pipe idle half of the time
+    // (profiles/r02_notes.md).  Same arithmetic per component as eval_u / psin_pi.
+    template <int W>
+    __device__ __forceinline__ static void eval_uw(const unsigned (&i)[W], double ph, const double* y, unsigned n, const char*, const double* aux,
+                                                   unsigned& slow, double (&out)[W])
+    {
+        const double MAGIC = 6755399441055744.0;
+        double x[W], qd[W], r[W], z[W], p[W], amp[W];
+        int q[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const double yn = (i[w] < (n - 1)) ? y[i[w] + 1] : 0.0;
+            x[w] = fma(yn, 0.02, ph);
+            amp[w] = aux[i[w]] * y[i[w]];
+        }
+#pragma unroll
+        for (int w = 0; w < W; w++) slow = max(slow, (unsigned)__double2hiint(x[w]) & 0x7fffffffu);
+#pragma unroll
+        for (int w = 0; w < W; w++) qd[w] = fma(x[w], 0.3183098861837907, MAGIC);
+#pragma unroll
+        for (int w = 0; w < W; w++) { q[w] = __double2loint(qd[w]); qd[w] -= MAGIC; }
+#pragma unroll
+        for (int w = 0; w < W; w++) r[w] = fma(qd[w], -3.141592653589793, x[w]);
+#pragma unroll
+        for (int w = 0; w < W; w++) r[w] = fma(qd[w], -1.2246467991473532e-16, r[w]);
+#pragma unroll
+        for (int w = 0; w < W; w++) r[w] = fma(qd[w], 2.9947698097183397e-33, r[w]);
+#pragma unroll
+        for (int w = 0; w < W; w++) { z[w] = r[w] * r[w]; p[w] = CYRK_FP_NS::g_sinpi.c[7]; }
+#pragma unroll
+        for (int k = 6; k >= 0; k--) {
+#pragma unroll
+            for (int w = 0; w < W; w++) p[w] = fma(p[w], z[w], CYRK_FP_NS::g_sinpi.c[k]);
+        }
+#pragma unroll
+        for (int w = 0; w < W; w++) z[w] *= r[w];
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const double res = fma(z[w], p[w], r[w]);
+            out[w] = amp[w] * __hiloint2double(__double2hiint(res) ^ (q[w] << 31), __double2loint(res));
+        }
+    }
 #endif
     __device__ __forceinline__ static double eval(unsigned i, double t, const double* y, unsigned n, const char*, const double* aux)
     {

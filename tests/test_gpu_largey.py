@@ -79,23 +79,46 @@ def test_largey_simple_and_unsupported_features():
         c.cysolve_ivp_batch("largey", (0.0, 10.0), big, args=[-0.5, 5000.0], events=[c.Event("y0")])
 
 
-@pytest.mark.parametrize("n", [700, 1500, 3000, 5000])
+@pytest.mark.parametrize("n", [700, 1500, 3000, 5000, 8192, 10000, 12000, 12500])
 def test_register_resident_kernel_sizes(oracle, n):
     """n_y = 700 / 1500 / 3000 exercise C = 2 / 4 / 8 components per thread with a ragged last block of components
-    (cta2_core.cuh); n_y = 5000 is past its limit and runs on the shared-memory/slab kernel (cta_core.cuh)."""
+    (cta2_core.cuh, every vector on chip); 5000 / 8192 / 10 000 / 12 000 take C = 12 / 16 / 20 / 24 with the stage
+    derivatives (and from C = 20 the aux table) in the L2-resident slab -- RK23 / RK45; DOP853 at those sizes, and
+    n_y = 12 500, run on the shared-memory/slab kernel (cta_core.cuh)."""
     rng = np.random.default_rng(11)
     B = 3
     y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (B, n)))
     args = [-0.5, float(n)]
     te = np.linspace(0, 10, 5)
-    for method, t_eval in (("RK45", None), ("RK23", te), ("DOP853", te)):
-        r = c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method=method, args=args, rtol=1e-6, atol=1e-8, t_eval=t_eval)
+    cases = (("RK45", None), ("RK23", te), ("DOP853", te)) if n <= 5000 else (("RK45", None), ("RK45", te), ("RK23", te))
+    for method, t_eval in cases:
         ref = oracle.solve("largey", (0.0, 10.0), y0[1], method, 1e-6, 1e-8, args=args, t_eval=t_eval)
-        v = r[1]
-        assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken), (method, n)
-        assert int(r.nfev[1]) == ref.nfev
-        assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
-        assert np.all(np.abs(v.y - ref.y) <= _tol(ref.y, 1e-6, 1e-8))
+        for strict in (False, True):
+            r = c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method=method, args=args, rtol=1e-6, atol=1e-8, t_eval=t_eval, strict_fp=strict)
+            v = r[1]
+            assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken), (method, n, strict)
+            assert int(r.nfev[1]) == ref.nfev
+            assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
+            assert np.all(np.abs(v.y - ref.y) <= _tol(ref.y, 1e-6, 1e-8))
+
+
+def test_large_slab_range_agrees_with_the_slab_kernel():
+    """4096 < n_y <= 12 288 on the register-resident kernel (option cta2_large, default) vs the shared-memory/slab kernel."""
+    rng = np.random.default_rng(13)
+    n, B = 10000, 5
+    y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (B, n)))
+    out = []
+    for large in (1, 0):
+        c.lib().cyrk_b200_set_option(b"cta2_large", large)
+        try:
+            out.append(c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method="RK45", args=[-0.5, float(n)], rtol=1e-6, atol=1e-8))
+        finally:
+            c.lib().cyrk_b200_set_option(b"cta2_large", 1)
+    a, b = out
+    assert (a.status == 1).all() and np.array_equal(a.steps_taken, b.steps_taken) and np.array_equal(a.n_rejected, b.n_rejected)
+    assert np.array_equal(a.size, b.size) and np.allclose(a.y_last, b.y_last, rtol=1e-9, atol=1e-12)
+    for i in range(B):
+        assert np.allclose(a[i].y, b[i].y, rtol=1e-9, atol=1e-12) and np.allclose(a[i].t, b[i].t, rtol=1e-10, atol=0)
 
 
 def test_both_cta_kernels_agree():
