@@ -1530,11 +1530,9 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     CU_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     int smem_per_sm = 0;
     CU_TRY(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
-    // Measured at n_y = 4096 (scripts/quick_c4_methods.py): the register-resident kernel wins for RK23 (16.7 vs 20.0 ms)
-    // and RK45 (5.3 vs 5.7 ms; 2.3x with a cheap right-hand side), but with DOP853's 16 stage vectors and 8 components per
-    // thread it spills (7.9 vs 6.1 ms): that one case stays on the shared-memory/slab kernel unless a feature only the
-    // register-resident kernel has (stored dense output, events) is requested.
-    const bool dop_c8 = a.method == CYRK_METHOD_DOP853 && N > (size_t)4 * cta2_max_block && !a.dense_output && a.n_events == 0;
+    // Measured at n_y = 4096 (scripts/quick_c4_methods.py, round 2): the register-resident kernel wins for every method
+    // (RK23 9.3 vs 18.4 ms, RK45 2.7 vs 5.4 ms, DOP853 3.6 vs 6.1 ms per 1184 trajectories), DOP853's nine slab-resident
+    // stage vectors included.  Option cta_kernel = 1 forces the shared-memory/slab kernel.
     bool whole_vector = false;           // user system in the whole-vector form: one thread evaluates it (slab kernel only)
     if (user_rhs) { int uny = 0, unx = 0, una = 0, une = 0; if (user_rhs_info(a.rhs_id, &uny, &unx, &una, &une) == 0) whole_vector = uny > CYRK_MAX_NY; }
     // n_y in (4096, 12 288]: the same kernel with the stage derivatives in the L2-resident slab (RK23 / RK45, no events,
@@ -1542,7 +1540,7 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     const bool cta2_slab_ok = N > (size_t)cta2_max_c_onchip * cta2_max_block && N <= (size_t)cta2_max_c * cta2_max_block &&
                               a.method != CYRK_METHOD_DOP853 && a.n_events == 0 && !dense && g_opt_cta2_large;
     const bool use_cta2 = !whole_vector && g_opt_cta_kernel != 1 &&
-                          ((N <= (size_t)cta2_max_c_onchip * cta2_max_block && !(dop_c8 && g_opt_cta_kernel == 0)) || cta2_slab_ok);
+                          (N <= (size_t)cta2_max_c_onchip * cta2_max_block || cta2_slab_ok);
     int cta2_C = 0;
     int block, grid;
     size_t smem;

@@ -9,7 +9,7 @@ y0d = torch.from_numpy(100.0 * (1 + 0.01 * rng.uniform(-1, 1, (B, n)))).cuda()
 ts = torch.tensor([0.0, 10.0], dtype=torch.float64, device="cuda")
 ar = torch.tensor([-0.5, float(n)], dtype=torch.float64, device="cuda")
 for method in ("RK23", "RK45", "DOP853"):
-    for kernel in (0, 1):
+    for kernel in (2, 1):
         c.lib().cyrk_b200_set_option(b"cta_kernel", kernel)
         res = None; best = 1e9
         for rep in range(3):
@@ -17,6 +17,6 @@ for method in ("RK23", "RK45", "DOP853"):
             best = min(best, res.kernel_ms)
         st = torch.as_tensor(res.steps_taken, device="cuda").float().mean().item()
         nr = torch.as_tensor(res.n_rejected, device="cuda").float().mean().item()
-        print(f"{method:7s} kernel={'cta2' if kernel == 0 else 'cta '} kernel_ms={best:.2f} steps={st:.1f} rejected={nr:.1f}", flush=True)
+        print(f"{method:7s} kernel={'cta2' if kernel == 2 else 'cta '} kernel_ms={best:.2f} steps={st:.1f} rejected={nr:.1f}", flush=True)
         res.close()
 c.lib().cyrk_b200_set_option(b"cta_kernel", 0)
