@@ -866,6 +866,10 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
             const int dir = (e < a.n_events && a.event_dirs) ? a.event_dirs[e] : 0;
             d += " -DCYRK_EV_DIR" + std::to_string(e) + "=" + std::to_string(dir > 0 ? 1 : dir < 0 ? -1 : 0);
         }
+        // RK23 with a small state: the detection solve sits just above 96 registers (4 CTAs of 128 threads per SM); capped
+        // for 6 CTAs (80 registers, a few bytes of spills) it measured 17.7 vs 19.6 ms on C3full at 1 Mi trajectories, 5 CTAs
+        // 18.1, 8 CTAs 18.8 (profiles/r02_c3full_minctas.log)
+        if (a.method == CYRK_METHOD_RK23 && pe->ny <= 4 && g_opt_block <= 0) d += " -DCYRK_USER_MINCTAS=6";
         disp_ev.ev_defs = d;
         int ctas_probe = 0;
         if (disp_ev.need_jit_id() == 0 && disp_ev.occupancy(a.method, VAR_EVDETECT, &ctas_probe, 128) == cudaSuccess) pe = &disp_ev;
