@@ -1539,10 +1539,10 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     // stage vectors included.  Option cta_kernel = 1 forces the shared-memory/slab kernel.
     bool whole_vector = false;           // user system in the whole-vector form: one thread evaluates it (slab kernel only)
     if (user_rhs) { int uny = 0, unx = 0, una = 0, une = 0; if (user_rhs_info(a.rhs_id, &uny, &unx, &una, &une) == 0) whole_vector = uny > CYRK_MAX_NY; }
-    // n_y in (4096, 12 288]: the same kernel with the stage derivatives in the L2-resident slab (RK23 / RK45, no events,
-    // no stored dense output); beyond that, and for DOP853, the shared-memory/slab kernel of cta_core.cuh
+    // n_y in (4096, 12 288]: the same kernel with the stage derivatives in the L2-resident slab (RK23 / RK45); beyond
+    // that, and for DOP853, the shared-memory/slab kernel of cta_core.cuh
     const bool cta2_slab_ok = N > (size_t)cta2_max_c_onchip * cta2_max_block && N <= (size_t)cta2_max_c * cta2_max_block &&
-                              a.method != CYRK_METHOD_DOP853 && a.n_events == 0 && !dense && g_opt_cta2_large;
+                              a.method != CYRK_METHOD_DOP853 && g_opt_cta2_large;
     const bool use_cta2 = !whole_vector && g_opt_cta_kernel != 1 &&
                           (N <= (size_t)cta2_max_c_onchip * cta2_max_block || cta2_slab_ok);
     int cta2_C = 0;
@@ -1556,7 +1556,8 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         p.atol0 = at[0];
     }
     if (a.n_events && !use_cta2) {
-        set_error("events on the CTA-per-trajectory path need the register-resident kernel (n_y <= %d)", 8 * cta2_max_block);
+        set_error("events on the CTA-per-trajectory path need the register-resident kernel (n_y <= %d; RK23 / RK45: n_y <= %d)",
+                  cta2_max_c_onchip * cta2_max_block, cta2_max_c * cta2_max_block);
         return -1;
     }
     p.n_events = (int)a.n_events;
@@ -1566,7 +1567,8 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         p.ev_max[e] = a.event_max ? (unsigned long long)a.event_max[e] : ~0ull;
     }
     if (dense && !use_cta2) {
-        set_error("stored dense output on the CTA-per-trajectory path needs the register-resident kernel (n_y <= %d); use t_eval", 8 * cta2_max_block);
+        set_error("stored dense output on the CTA-per-trajectory path needs the register-resident kernel (n_y <= %d; RK23 / RK45: n_y <= %d); use t_eval",
+                  cta2_max_c_onchip * cta2_max_block, cta2_max_c * cta2_max_block);
         return -1;
     }
     if (use_cta2) {

@@ -1,5 +1,6 @@
-// inst_cta.cu -- instantiates the CTA-per-trajectory kernels (both large built-in problems, three methods) for
-// ONE floating-point mode: compiled twice by the Makefile (-DCYRK_FP_NS=fast -fmad=true / strict -fmad=false).
+// inst_cta.cu -- instantiates the CTA-per-trajectory kernels (one large built-in problem per translation unit, three
+// methods) for ONE floating-point mode: compiled four times by the Makefile (-DCYRK_CTA_PART=0|1 x
+// -DCYRK_FP_NS=fast -fmad=true / strict -fmad=false).
 #include "cta_core.cuh"
 #include "cta2_core.cuh"
 #include "problems_builtin.cuh"
@@ -52,12 +53,12 @@ cudaError_t by_c(int C, const CtaParams& p, int grid, int block, size_t smem, cu
     case 2: return go2<Prob, METHOD, 2>(p, grid, block, smem, s);
     case 4: return go2<Prob, METHOD, 4>(p, grid, block, smem, s);
     case 8: return go2<Prob, METHOD, 8>(p, grid, block, smem, s);
-    // n_y in (4096, 12 288]: derivatives in the L2-resident slab; RK23 / RK45 without events (DOP853's 16 vectors of
-    // 96 KB x 148 CTAs would not stay in L2; cta_core.cuh takes it)
-    case 12: if constexpr (METHOD != METHOD_DOP853) return go2e<Prob, METHOD, 12, false>(p, grid, block, smem, s); else return cudaErrorInvalidValue;
-    case 16: if constexpr (METHOD != METHOD_DOP853) return go2e<Prob, METHOD, 16, false>(p, grid, block, smem, s); else return cudaErrorInvalidValue;
-    case 20: if constexpr (METHOD != METHOD_DOP853) return go2e<Prob, METHOD, 20, false>(p, grid, block, smem, s); else return cudaErrorInvalidValue;
-    case 24: if constexpr (METHOD != METHOD_DOP853) return go2e<Prob, METHOD, 24, false>(p, grid, block, smem, s); else return cudaErrorInvalidValue;
+    // n_y in (4096, 12 288]: derivatives in the L2-resident slab; RK23 / RK45 (DOP853's 16 vectors of 96 KB x 148 CTAs
+    // would not stay in L2; cta_core.cuh takes it)
+    case 12: if constexpr (METHOD != METHOD_DOP853) return go2<Prob, METHOD, 12>(p, grid, block, smem, s); else return cudaErrorInvalidValue;
+    case 16: if constexpr (METHOD != METHOD_DOP853) return go2<Prob, METHOD, 16>(p, grid, block, smem, s); else return cudaErrorInvalidValue;
+    case 20: if constexpr (METHOD != METHOD_DOP853) return go2<Prob, METHOD, 20>(p, grid, block, smem, s); else return cudaErrorInvalidValue;
+    case 24: if constexpr (METHOD != METHOD_DOP853) return go2<Prob, METHOD, 24>(p, grid, block, smem, s); else return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
     }
 }
@@ -74,17 +75,42 @@ cudaError_t by_method2(int method, int C, const CtaParams& p, int grid, int bloc
 }  // namespace
 }  // namespace CYRK_FP_NS
 
+// One translation unit per built-in large problem (CYRK_CTA_PART: 0 = largey, 1 = largey_simple; they compile in
+// parallel); part 0 also holds the dispatch by rhs id and the problem-independent kernels.
+#ifndef CYRK_CTA_PART
+#error "compile with -DCYRK_CTA_PART=0|1"
+#endif
+#define CYRK_CAT3_(a, b, c) a##b##c
+#define CYRK_CAT3(a, b, c) CYRK_CAT3_(a, b, c)
+#if CYRK_CTA_PART == 0
+using CtaPartProb = ProbLargeY;
+#else
+using CtaPartProb = ProbLargeYSimple;
+#endif
+cudaError_t CYRK_CAT3(cta_launch_part_, CYRK_FP_NS, CYRK_CTA_PART)(int method, const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
+{
+    return CYRK_FP_NS::by_method<CtaPartProb>(method, p, grid, block, smem, s);
+}
+cudaError_t CYRK_CAT3(cta2_launch_part_, CYRK_FP_NS, CYRK_CTA_PART)(int method, int C, const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
+{
+    return CYRK_FP_NS::by_method2<CtaPartProb>(method, C, p, grid, block, smem, s);
+}
+
+#if CYRK_CTA_PART == 0
+cudaError_t CYRK_CAT3(cta_launch_part_, CYRK_FP_NS, 1)(int method, const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s);
+cudaError_t CYRK_CAT3(cta2_launch_part_, CYRK_FP_NS, 1)(int method, int C, const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s);
+
 cudaError_t CYRK_CAT2(cta_launch_, CYRK_FP_NS)(int rhs_id, int method, const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
 {
-    if (rhs_id == RHS_LARGEY) return CYRK_FP_NS::by_method<ProbLargeY>(method, p, grid, block, smem, s);
-    if (rhs_id == RHS_LARGEY_SIMPLE) return CYRK_FP_NS::by_method<ProbLargeYSimple>(method, p, grid, block, smem, s);
+    if (rhs_id == RHS_LARGEY) return CYRK_CAT3(cta_launch_part_, CYRK_FP_NS, 0)(method, p, grid, block, smem, s);
+    if (rhs_id == RHS_LARGEY_SIMPLE) return CYRK_CAT3(cta_launch_part_, CYRK_FP_NS, 1)(method, p, grid, block, smem, s);
     return cudaErrorInvalidValue;
 }
 
 cudaError_t CYRK_CAT2(cta2_launch_, CYRK_FP_NS)(int rhs_id, int method, int C, const CtaParams& p, int grid, int block, size_t smem, cudaStream_t s)
 {
-    if (rhs_id == RHS_LARGEY) return CYRK_FP_NS::by_method2<ProbLargeY>(method, C, p, grid, block, smem, s);
-    if (rhs_id == RHS_LARGEY_SIMPLE) return CYRK_FP_NS::by_method2<ProbLargeYSimple>(method, C, p, grid, block, smem, s);
+    if (rhs_id == RHS_LARGEY) return CYRK_CAT3(cta2_launch_part_, CYRK_FP_NS, 0)(method, C, p, grid, block, smem, s);
+    if (rhs_id == RHS_LARGEY_SIMPLE) return CYRK_CAT3(cta2_launch_part_, CYRK_FP_NS, 1)(method, C, p, grid, block, smem, s);
     return cudaErrorInvalidValue;
 }
 
@@ -105,5 +131,6 @@ int cta_num_vectors(int method)
     return method == METHOD_RK23 ? 2 + TabRK23::NK_DENSE : method == METHOD_RK45 ? 2 + TabRK45::NK_DENSE : 2 + TabDOP853::NK_DENSE;
 }
 #endif
+#endif  // CYRK_CTA_PART == 0
 
 }  // namespace cyrk

@@ -52,7 +52,7 @@ extern "C" {
 #define CYRK_RHS_PENDULUM          6
 #define CYRK_RHS_ARBITRARY_ARGS    7
 #define CYRK_RHS_PENDULUM_PREEVAL  8
-#define CYRK_RHS_LARGEY            9   /* CTA-per-trajectory path, any n_y (events / dense output: n_y <= 4096) */
+#define CYRK_RHS_LARGEY            9   /* CTA-per-trajectory path, any n_y (events / dense output: n_y <= 12288, DOP853: <= 4096) */
 #define CYRK_RHS_LARGEY_SIMPLE     10  /* CTA-per-trajectory path, any n_y */
 #define CYRK_RHS_PENDULUM_DRAG     11
 #define CYRK_RHS_DENSE_KAT         12
@@ -268,7 +268,7 @@ size_t   cyrk_b200_get_lazy_d2h_bytes(void* h); /* copied afterwards by getters 
 /* Tuning knobs (process-wide): "refill_min" (1..32), "block" (threads per CTA of the thread-per-trajectory kernels,
  * 0 = by occupancy), "ctas_per_sm" (0 = occupancy API), "prep" (start-up kernel: -1 auto / 0 / 1), "root_batch" (1..32),
  * "cta_kernel" (0 = register-resident CTA kernel where it applies, 1 = shared-memory/slab kernel), "cta_block",
- * "cta_smem_vecs" (slab kernel only), "pipe_chunk" (trajectories per chunk of the pipelined host-I/O path),
+ * "cta_smem_vecs" (slab kernel only), "cta2_large" (1 = register-resident kernel also for 4096 < n_y <= 12288), "pipe_chunk" (trajectories per chunk of the pipelined host-I/O path),
  * "pipe_taper" (short first/last chunks, 0/1), "pipe_min" (smallest host-buffer final-state batch that takes the pipelined path;
  * default 256 Ki, 0 = never), "two_pass" (dense_output / t_eval without events or extras: 1 = step-parallel
  * interpolants when dense_output is set [default], 2 = also for t_eval alone, 0 = always the per-trajectory kernel; the

@@ -1,11 +1,8 @@
 #!/bin/bash
-P=${1:-r02_s25}
+P=${1:-r02_s28}
 O=gpurun_out
 mkdir -p $O
-: > $O/${P}_c3full_minctas.log
-for m in 0 5 6 8; do
-  if [ $m = 0 ]; then D=""; else D="-DCYRK_USER_MINCTAS=$m"; fi
-  echo "== CYRK_USER_MINCTAS=$m" >> $O/${P}_c3full_minctas.log
-  CYRK_B200_DEBUG=1 CYRK_B200_NVRTC_DEFINES="$D" python scripts/quick_c3full.py 2>&1 | grep -v "events_two_pass=0\|events_static=0" | grep "C3full\|CTAs/SM" | sort -u | tail -4 >> $O/${P}_c3full_minctas.log
-done
-cat $O/${P}_c3full_minctas.log
+timeout 1800 python -m pytest tests/test_gpu_largey.py tests/test_user_rhs.py -m gpu -q -x > $O/${P}_gpu_tests.log 2>&1
+tail -8 $O/${P}_gpu_tests.log
+python scripts/quick_c4.py 2>&1 | tee $O/${P}_c4.log
+echo done

@@ -72,11 +72,15 @@ def test_largey_simple_and_unsupported_features():
     assert np.allclose(r.y_last[:, 0], 100.0, atol=5e-3) and np.all(r.y_last[:, 1:] == 100.0)
     with pytest.raises(c.CyrkB200Error):        # no extra outputs on the CTA path
         c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, args=[-0.5, float(n)], num_extra=1)
-    big = 100.0 * np.ones((2, 5000))            # stored dense output / events need the register-resident kernel (n_y <= 4096)
+    # stored dense output / events need the register-resident kernel: n_y <= 4096 for DOP853, n_y <= 12 288 for RK23 / RK45
+    big = 100.0 * np.ones((2, 5000))
     with pytest.raises(c.CyrkB200Error):
-        c.cysolve_ivp_batch("largey", (0.0, 10.0), big, args=[-0.5, 5000.0], dense_output=True)
+        c.cysolve_ivp_batch("largey", (0.0, 10.0), big, method="DOP853", args=[-0.5, 5000.0], dense_output=True)
     with pytest.raises(c.CyrkB200Error):
-        c.cysolve_ivp_batch("largey", (0.0, 10.0), big, args=[-0.5, 5000.0], events=[c.Event("y0")])
+        c.cysolve_ivp_batch("largey", (0.0, 10.0), big, method="DOP853", args=[-0.5, 5000.0], events=[c.Event("y0")])
+    huge = 100.0 * np.ones((2, 12500))
+    with pytest.raises(c.CyrkB200Error):
+        c.cysolve_ivp_batch("largey", (0.0, 10.0), huge, args=[-0.5, 12500.0], events=[c.Event("y0")])
 
 
 @pytest.mark.parametrize("n", [700, 1500, 3000, 5000, 8192, 10000, 12000, 12500])
@@ -176,10 +180,9 @@ def test_cta_results_are_bitwise_reproducible():
         r.close()
 
 
-@pytest.mark.parametrize("method", ["RK23", "RK45", "DOP853"])
-@pytest.mark.parametrize("n", [130, 1500])
+@pytest.mark.parametrize("method,n", [(m, n) for m in ("RK23", "RK45", "DOP853") for n in (130, 1500)] + [("RK45", 5000), ("RK23", 10000)])
 def test_cta_dense_output_matches_oracle(oracle, method, n):
-    """dense_output=True on the CTA path: sol(t) from the stored interpolants vs the oracle's CySolverResult::call, forward
+    """(n_y = 5000 / 10 000: the slab-extended range of the register-resident kernel, C = 12 / 20.)  dense_output=True on the CTA path: sol(t) from the stored interpolants vs the oracle's CySolverResult::call, forward
     and backward, with and without t_eval; nfev includes DOP853's three extra evaluations per interpolant."""
     rng = np.random.default_rng(31)
     B = 3
@@ -236,10 +239,9 @@ def test_cta_failure_statuses_match_oracle(oracle):
             c.lib().cyrk_b200_set_option(b"cta_kernel", 0)
 
 
-@pytest.mark.parametrize("method", ["RK23", "RK45", "DOP853"])
-@pytest.mark.parametrize("n", [130, 1500])
+@pytest.mark.parametrize("method,n", [(m, n) for m in ("RK23", "RK45", "DOP853") for n in (130, 1500)] + [("RK23", 5000), ("RK45", 10000)])
 def test_cta_events_match_oracle(oracle, method, n):
-    """Events on the CTA path (register-resident kernel): the reference's built-in event functions on largey --
+    """(n_y = 5000 / 10 000: the slab-extended range of the register-resident kernel, C = 12 / 20.)  Events on the CTA path (register-resident kernel): the reference's built-in event functions on largey --
     step functions, so every search runs the reference's special cases (f(xa) == 0, f(xb) == 0, bisection on a
     discontinuity) --, non-terminal and terminal, with t_eval and stored dense output, vs the oracle."""
     rng = np.random.default_rng(51)
