@@ -87,6 +87,7 @@ void registry_init()
 static int g_opt_refill_min = 0;      // 0 = automatic (1 with prep, 4 without)
 static int g_opt_prep = -1;           // -1 = automatic (n_traj >= 2 Mi), 1 = always, 0 = never
 static int g_opt_block = 0;            // threads per CTA of the thread-per-trajectory kernels; 0 = pick by occupancy (128 or 96)
+static int g_opt_small_cta = 0;       // 1: DOP853 user systems with 16 < n_y <= 32 run a warp per trajectory (cta_core.cuh) instead of a thread (measured 4x slower)
 static int g_opt_cta2_large = 1;      // register-resident CTA kernel for 4096 < n_y <= 12 288 (derivatives in the L2 slab); 0: cta_core.cuh
 static int g_opt_cta_smem_vecs = -1;  // CTA path: working vectors kept in shared memory (-1 = as many as fit)
 static int g_opt_cta_block = 0;       // CTA path: threads per CTA (0 = by n_y)
@@ -1538,7 +1539,7 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     // (RK23 9.3 vs 18.4 ms, RK45 2.7 vs 5.4 ms, DOP853 3.6 vs 6.1 ms per 1184 trajectories), DOP853's nine slab-resident
     // stage vectors included.  Option cta_kernel = 1 forces the shared-memory/slab kernel.
     bool whole_vector = false;           // user system in the whole-vector form: one thread evaluates it (slab kernel only)
-    if (user_rhs) { int uny = 0, unx = 0, una = 0, une = 0; if (user_rhs_info(a.rhs_id, &uny, &unx, &una, &une) == 0) whole_vector = uny > CYRK_MAX_NY; }
+    if (user_rhs) { int uny = 0, unx = 0, una = 0, une = 0; if (user_rhs_info(a.rhs_id, &uny, &unx, &una, &une) == 0) whole_vector = uny > 0; }     // (registered with its n_y: the whole-vector form; component-wise systems register n_y = 0)
     // n_y in (4096, 12 288]: the same kernel with the stage derivatives in the L2-resident slab (RK23 / RK45); beyond
     // that, and for DOP853, the shared-memory/slab kernel of cta_core.cuh
     const bool cta2_slab_ok = N > (size_t)cta2_max_c_onchip * cta2_max_block && N <= (size_t)cta2_max_c * cta2_max_block &&
@@ -1594,13 +1595,13 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         // slab) changes the kernel time by < 2 %, but TWO 512-thread CTAs per SM beat one 1024-thread CTA by 10 %
         // (one CTA's barrier waits hide behind the other's arithmetic).  So: 512 threads, and only as many vectors in
         // shared memory as still leave room for two CTAs per SM.
-        block = N <= 256 ? 128 : N <= 1024 ? 256 : 512;
+        block = N <= 32 ? 32 : N <= 64 ? 64 : N <= 256 ? 128 : N <= 1024 ? 256 : 512;      // (<= 64: a warp or two per trajectory)
         if (g_opt_cta_block > 0) block = g_opt_cta_block;
         const size_t fit2 = ((size_t)smem_per_sm / 2 > 2048 + vec_bytes) ? ((size_t)smem_per_sm / 2 - 2048) / vec_bytes : 0;
         p.n_smem_vec = (unsigned)std::min<size_t>({fit, fit2, (size_t)nvec});
         if (g_opt_cta_smem_vecs >= 0) p.n_smem_vec = std::min<unsigned>((unsigned)std::min<size_t>(fit, (size_t)nvec), (unsigned)g_opt_cta_smem_vecs);
         smem = (size_t)p.n_smem_vec * vec_bytes;
-        int per_sm = (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)(2048 / block), ((size_t)smem_per_sm) / (smem + 2048)}));
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>({(size_t)(block <= 64 ? 32 : 8), (size_t)(2048 / block), ((size_t)smem_per_sm) / (smem + 2048)}));
         grid = (int)std::min<unsigned long long>((unsigned long long)device_sm_count(h->device) * per_sm, B);
         const size_t n_glob = (size_t)nvec - p.n_smem_vec;
         if (h->d_scratch.ensure((size_t)grid * (n_glob + 2) * vec_bytes)) return -1;
@@ -1776,6 +1777,20 @@ static int solve_impl(Handle* h, const SolveArgs& a)
             set_error("right-hand side %d produces %d extra outputs but num_extra = %zu", a.rhs_id, disp.nextra, a.num_extra);
             return -1;
         }
+        if (solve_cta_path(h, a, fp)) return -1;
+        h->solved = true;
+        return 0;
+    }
+    // DOP853 with 16 < n_y <= 32 state components: one thread holds 16 x n_y stage derivatives (up to 4.3 KB of local
+    // memory; 8.7 % of the FP64 peak at n_y = 32).  Option small_cta = 1 runs a WARP per trajectory instead (the
+    // CTA-per-trajectory kernel of cta_core.cuh with 32-thread CTAs, the whole-vector function evaluated by lane 0, the stage
+    // arithmetic spread over the lanes).  Measured (profiles/r02_medium_ny_small_cta.log): 28.6 vs 7.2 ms at n_y = 32,
+    // 29.8 vs 3.4 ms at n_y = 24 -- the serial right-hand side on one lane and that kernel's barrier per loop cost far more
+    // than the spills -- so the default stays the thread-per-trajectory kernel.
+    if (a.rhs_id >= CYRK_RHS_USER_BASE && g_opt_small_cta && a.method == CYRK_METHOD_DOP853 && disp.ny > 16 && disp.ny <= CYRK_MAX_NY &&
+        (size_t)disp.ny == a.n_y && a.n_events == 0 && !a.dense_output && a.num_extra == 0 && disp.nextra == 0 &&
+        !(a.flags & (CYRK_FLAG_T_EVAL_PER_TRAJ | CYRK_FLAG_TOL_PER_TRAJ)) &&
+        (a.n_args == 0 ? disp.nargs_dbl == 0 : a.args_len == (size_t)disp.nargs_dbl * 8)) {
         if (solve_cta_path(h, a, fp)) return -1;
         h->solved = true;
         return 0;
@@ -2248,6 +2263,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "events_static")) { g_opt_events_static = value; return 0; }
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
     if (!strcmp(name, "cta2_large")) { g_opt_cta2_large = value; return 0; }
+    if (!strcmp(name, "small_cta")) { g_opt_small_cta = value; return 0; }
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
     if (!strcmp(name, "cta_kernel")) { g_opt_cta_kernel = value; return 0; }
     if (!strcmp(name, "pipe_taper")) { g_opt_pipe_taper = value; return 0; }

@@ -89,7 +89,10 @@ constexpr int cta2_choose_c(unsigned long long n)
     return n <= 512 ? 1 : n <= 1024 ? 2 : n <= 2048 ? 4 : n <= 4096 ? 8 : n <= 6144 ? 12 : n <= 8192 ? 16 : n <= 10240 ? 20 : n <= 12288 ? 24 : 0;
 }
 // doubles of state per thread kept in registers: y_old + NREG derivative vectors
-constexpr int cta2_reg_doubles(int C) { return C >= 20 ? C : C >= 12 ? 2 * C : C >= 8 ? 32 : 40; }
+#ifndef CYRK_CTA2_REGD_LARGE      // experiment knob: multiple of C doubles kept in registers for C >= 20
+#define CYRK_CTA2_REGD_LARGE 1
+#endif
+constexpr int cta2_reg_doubles(int C) { return C >= 20 ? CYRK_CTA2_REGD_LARGE * C : C >= 12 ? 2 * C : C >= 8 ? 32 : 40; }
 constexpr int cta2_nkd(int method) { return method == 3 ? 4 : method == 4 ? 7 : 16; }      // RK23 / RK45 / DOP853 (+3 dense)
 constexpr int cta2_nreg(int nkd, int C) { return (cta2_reg_doubles(C) / C - 1) < nkd ? (cta2_reg_doubles(C) / C - 1) : nkd; }
 constexpr int cta2_sm_slots(int C) { return (227 * 1024 - 1024) / (C * cta2_threads(C) * 8); }

@@ -84,3 +84,38 @@ def test_spring_chain_matches_oracle(oracle, ny, method, strict):
         assert np.all(np.abs(w.y - ref2.y) <= tol(ref2.y))
         assert np.all(np.abs(dense[i].T - ref2.dense) <= tol(ref2.dense) + 1e-9)
     assert same == B if strict else same >= B - 1
+
+
+@pytest.mark.parametrize("ny", [18, 24, 32])
+def test_dop853_warp_per_trajectory_route_agrees_with_the_thread_path(oracle, ny):
+    """Option small_cta = 1: DOP853 with 16 < n_y <= 32 (final state / rows / t_eval, no events, no dense store) runs a warp
+    per trajectory (cta_core.cuh with 32-thread CTAs, lane 0 evaluates the whole-vector function) instead of spilling
+    16 x n_y stage derivatives per thread.  Measured 4x slower than the thread-per-trajectory kernel, so it is off by
+    default; the route stays tested: equal step counts, states within the bar of each other and of the oracle."""
+    m = ny // 2
+    u = c.UserRHS(chain_source(m), f"chain{ny}", n_y=ny, args_bytes=16)
+    B = 40
+    y0, args = chain_inputs(m, B, 90 + ny)
+    cb = chain_callback(oracle, m)
+    rtol, atol = 1e-8, 1e-10
+    te = np.linspace(0.0, 6.0, 13)
+    out = {}
+    for small in (1, 0):
+        c.lib().cyrk_b200_set_option(b"small_cta", small)
+        try:
+            out[small] = (c.cysolve_ivp_batch(u, (0.0, 6.0), y0, method="DOP853", args=args, rtol=rtol, atol=atol, store="rows",
+                                              expected_size=2048, strict_fp=True),
+                          c.cysolve_ivp_batch(u, (0.0, 6.0), y0, method="DOP853", args=args, rtol=rtol, atol=atol, t_eval=te, strict_fp=True))
+        finally:
+            c.lib().cyrk_b200_set_option(b"small_cta", 0)
+    (a_rows, a_te), (b_rows, b_te) = out[1], out[0]
+    assert (a_rows.status == 1).all() and np.array_equal(a_rows.steps_taken, b_rows.steps_taken)
+    assert np.array_equal(a_rows.n_rejected, b_rows.n_rejected) and np.array_equal(a_rows.nfev, b_rows.nfev)
+    tol = lambda y: 10 * rtol * np.abs(y) + 10 * atol
+    assert np.all(np.abs(a_rows.y_last - b_rows.y_last) <= tol(b_rows.y_last))
+    for i in (0, B // 2, B - 1):
+        ref = oracle.solve(cb, (0.0, 6.0), y0[i], "DOP853", rtol, atol, args=args[i], num_extra=0, t_eval=te)
+        w = a_te[i]
+        assert w.size == ref.size == te.size and np.all(np.abs(w.y - ref.y) <= tol(ref.y))
+        assert np.all(np.abs(w.y - b_te[i].y) <= tol(ref.y))
+        assert (a_rows[i].size, a_rows[i].steps_taken) == (b_rows[i].size, b_rows[i].steps_taken)
