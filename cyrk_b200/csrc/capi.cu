@@ -87,6 +87,8 @@ void registry_init()
 static int g_opt_refill_min = 0;      // 0 = automatic (1 with prep, 4 without)
 static int g_opt_prep = -1;           // -1 = automatic (n_traj >= 2 Mi), 1 = always, 0 = never
 static int g_opt_block = 0;            // threads per CTA of the thread-per-trajectory kernels; 0 = pick by occupancy (128 or 96)
+static int g_opt_cta2_per_sm = 0;     // register-resident CTA kernel: cap on CTAs per SM (0 = the hardware's 32; registers allow 16
+                                      // 32-thread CTAs: n_y = 32, DOP853: 3.8 vs 6.4 ms with the former cap of 8, profiles/r02_medium_ny_component_wise.log)
 static int g_opt_small_cta = 0;       // 1: DOP853 user systems with 16 < n_y <= 32 run a warp per trajectory (cta_core.cuh) instead of a thread (measured 4x slower)
 static int g_opt_cta2_large = 1;      // register-resident CTA kernel for 4096 < n_y <= 12 288 (derivatives in the L2 slab); 0: cta_core.cuh
 static int g_opt_cta_smem_vecs = -1;  // CTA path: working vectors kept in shared memory (-1 = as many as fit)
@@ -1582,7 +1584,7 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         // registers: the kernel is compiled for <= 128 per thread (__launch_bounds__(512, 1))
         const size_t by_regs = std::max<size_t>(1, (size_t)65536 / ((size_t)128 * block));
         const size_t by_smem = std::max<size_t>(1, (size_t)smem_per_sm / (smem + 2048));
-        const int per_sm = (int)std::min<size_t>({(size_t)8, by_regs, by_smem});
+        const int per_sm = (int)std::min<size_t>({(size_t)(g_opt_cta2_per_sm > 0 ? g_opt_cta2_per_sm : 32), by_regs, by_smem});
         grid = (int)std::min<unsigned long long>((unsigned long long)device_sm_count(h->device) * per_sm, B);
         if (h->d_scratch.ensure((size_t)grid * (size_t)cta2_slab_vectors(nkd, cta2_C) * V * 8)) return -1;
         p.scratch = h->d_scratch.as<double>();
@@ -2264,6 +2266,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "cta_smem_vecs")) { g_opt_cta_smem_vecs = value; return 0; }
     if (!strcmp(name, "cta2_large")) { g_opt_cta2_large = value; return 0; }
     if (!strcmp(name, "small_cta")) { g_opt_small_cta = value; return 0; }
+    if (!strcmp(name, "cta2_per_sm")) { g_opt_cta2_per_sm = value; return 0; }
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
     if (!strcmp(name, "cta_kernel")) { g_opt_cta_kernel = value; return 0; }
     if (!strcmp(name, "pipe_taper")) { g_opt_pipe_taper = value; return 0; }
