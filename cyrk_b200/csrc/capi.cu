@@ -1269,8 +1269,18 @@ static size_t stream_chunk_for(const SolveArgs& a, const Dispatch* pe)
     if (g_opt_stream_chunk > 0) chunk = (size_t)g_opt_stream_chunk;
     else {
         if ((double)B * (double)per_traj < 1073741824.0) return 0;           // < 1 GiB of arena: one launch
-        chunk = std::min<size_t>((size_t)(3221225472.0 / (double)per_traj), B / 4);
-        chunk = std::max<size_t>(chunk / 1024 * 1024, 16384);
+        // Chunks as large as an eighth of the free device memory allows (two sub-handles hold one arena each; between 3 and
+        // 16 GiB), at most half the batch: every chunk is a persistent kernel with its own drain phase, so fewer chunks
+        // solve faster (C3full, 4 Mi trajectories end to end: 8 chunks 91.5 ms, 4: 87.0, 2: 85.5;
+        // profiles/r02_c3full_e2e_chunks.log) while half the batch still overlaps its copy-out with the other half's solve.
+        size_t free_b = 0, total_b = 0;
+        double cap = 3221225472.0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) cap = std::min(17179869184.0, std::max(cap, (double)free_b / 8.0));
+        else cudaGetLastError();
+        const size_t max_chunk = std::max<size_t>((size_t)(cap / (double)per_traj), 16384);
+        const size_t nch = std::max<size_t>(2, (B + max_chunk - 1) / max_chunk);          // equal chunks, at least two
+        chunk = std::max<size_t>(((B + nch - 1) / nch + 1023) / 1024 * 1024, 16384);
+        return B > chunk ? chunk : 0;
     }
     return (B >= 2 * chunk) ? chunk : 0;
 }

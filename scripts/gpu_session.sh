@@ -1,8 +1,9 @@
 #!/bin/bash
-P=${1:-r02_s31}
+P=${1:-r02_s34}
 O=gpurun_out
 mkdir -p $O
-timeout 1200 python -m pytest tests/test_gpu_medium_ny.py -m gpu -q -x > $O/${P}_gpu_tests.log 2>&1
-tail -8 $O/${P}_gpu_tests.log
-timeout 900 python scripts/bench_medium_ny.py 2>&1 | tail -5 | tee $O/${P}_medium_ny.log
+timeout 1200 python -m pytest tests/test_gpu_streaming.py tests/test_gpu_boundary.py -m gpu -q -x > $O/${P}_gpu_tests.log 2>&1
+tail -4 $O/${P}_gpu_tests.log
+python scripts/quick_c3full_e2e.py 2>&1 | head -1 | tee $O/${P}_c3full_e2e.log
+python scripts/check_streaming_full.py 2>&1 | tail -12 | tee $O/${P}_streaming_full.log
 echo done
