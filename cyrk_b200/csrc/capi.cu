@@ -81,11 +81,13 @@ void registry_init()
 // ------------------------------------------------------------------------------------------------
 // options
 // ------------------------------------------------------------------------------------------------
-// Measured on B200 (profiles/r01_notes.md): with the start-up state precomputed by rk_prep_kernel a refill is a
-// handful of loads, so lanes refill immediately (refill_min 1); that wins from ~2 Mi trajectories up (-6 % at
-// 8 Mi).  Below that the extra launch costs more than it saves and inline set-up with refill_min 4 is best.
+// Measured on B200: with the start-up state precomputed by rk_prep_kernel a refill is a handful of loads, so lanes
+// refill immediately (refill_min 1).  Round 1 (profiles/r01_notes.md) found that to win from ~2 Mi trajectories up; with
+// the round-2 kernels (shared args in the parameter block) it wins from 256 Ki: 0.773 vs 0.785 ms there, 1.34 vs 1.42 at
+// 512 Ki, 2.46 vs 2.65 at 1 Mi, 4.71 vs 5.10 at 2 Mi (profiles/r02_c1_prep_by_batch.log).  Below that the extra launch
+// costs what it saves and inline set-up with refill_min 4 stays.
 static int g_opt_refill_min = 0;      // 0 = automatic (1 with prep, 4 without)
-static int g_opt_prep = -1;           // -1 = automatic (n_traj >= 2 Mi), 1 = always, 0 = never
+static int g_opt_prep = -1;           // -1 = automatic (n_traj >= 256 Ki), 1 = always, 0 = never
 static int g_opt_block = 0;            // threads per CTA of the thread-per-trajectory kernels; 0 = pick by occupancy (128 or 96)
 static int g_opt_cta2_per_sm = 0;     // register-resident CTA kernel: cap on CTAs per SM (0 = the hardware's 32; registers allow 16
                                       // 32-thread CTAs: n_y = 32, DOP853: 3.8 vs 6.4 ms with the former cap of 8, profiles/r02_medium_ny_component_wise.log)
@@ -811,7 +813,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         p.ev_max[e] = a.event_max ? (unsigned long long)a.event_max[e] : ~0ull;
     }
     p.root_batch = std::min(32, std::max(1, g_opt_root_batch));
-    const bool use_prep = g_opt_prep < 0 ? (B >= (size_t(1) << 21)) : (g_opt_prep != 0);
+    const bool use_prep = g_opt_prep < 0 ? (B >= (size_t(1) << 18)) : (g_opt_prep != 0);
     p.refill_min = g_opt_refill_min > 0 ? std::min(32, g_opt_refill_min) : (use_prep ? 1 : 4);
 
     CU_TRY(cudaEventRecord(h->ev_begin, h->stream));
@@ -976,6 +978,10 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         BatchParams& pa = p_steps;
         pa = p;
         pa.t_eval = nullptr; pa.n_t_eval = 0; pa.dense_output = 0;
+        // (the recording solve keeps round 1's threshold for the start-up kernel: at 256 Ki Lorenz/DOP853 trajectories it
+        // measured 10.0 ms with it against 9.0 without, profiles/r02_prep_threshold_other_workloads.log)
+        const bool use_prep = g_opt_prep < 0 ? (B >= (size_t(1) << 21)) : (g_opt_prep != 0);
+        pa.refill_min = g_opt_refill_min > 0 ? std::min(32, g_opt_refill_min) : (use_prep ? 1 : 4);
         const size_t RA = CYRK_STEP_REC_DOUBLES(NY);
         for (int pass = 0; pass < 2; pass++) {
             scap = (scap + 31) / 32 * 32;       // whole warps per trajectory in step_dense_kernel
