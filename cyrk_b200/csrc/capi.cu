@@ -978,9 +978,12 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
         BatchParams& pa = p_steps;
         pa = p;
         pa.t_eval = nullptr; pa.n_t_eval = 0; pa.dense_output = 0;
-        // (the recording solve keeps round 1's threshold for the start-up kernel: at 256 Ki Lorenz/DOP853 trajectories it
-        // measured 10.0 ms with it against 9.0 without, profiles/r02_prep_threshold_other_workloads.log)
-        const bool use_prep = g_opt_prep < 0 ? (B >= (size_t(1) << 21)) : (g_opt_prep != 0);
+        // (the recording solve runs with inline set-up and refill_min 4 unless the options say otherwise: what costs is
+        // the immediate refill that comes with the start-up kernel -- Lorenz/DOP853, both passes, 2 Mi trajectories:
+        // refill_min 1 / 2 / 4 / 8 = 82.2 / 70.4 / 68.2 / 69.0 ms, start-up kernel + refill_min 4: 67.8; 256 Ki 9.0 vs 10.0,
+        // 1 Mi 34.4 vs 40.4 -- profiles/r02_c2full_refill_min.log, r02_prep_c2full.log.  Round 1's automatic rule had
+        // switched to the start-up kernel + refill_min 1 from 2 Mi.)
+        const bool use_prep = g_opt_prep > 0;
         pa.refill_min = g_opt_refill_min > 0 ? std::min(32, g_opt_refill_min) : (use_prep ? 1 : 4);
         const size_t RA = CYRK_STEP_REC_DOUBLES(NY);
         for (int pass = 0; pass < 2; pass++) {
