@@ -46,7 +46,7 @@ sys.path.insert(0, ROOT)
 # DRAM traffic per launch of the dominant kernel from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum),
 # same workload/batch as the bench line.  (algorithmic for C5: y0 16 B + start-up record 40 B in, 44 B out per
 # trajectory = 839 MB)
-NCU_TRAFFIC = {"C5": (890.8e6, "profiles/r02_ncu_c5_lv_rk45.txt")}
+NCU_TRAFFIC = {"C5": (890.1e6, "profiles/r02_final_ncu_c5_lv_rk45.txt")}
 
 # F_attempt(m) = n_y*c_m + E_m*F_rhs + s   
 C_M = {"RK23": 25, "RK45": 62, "DOP853": 167}

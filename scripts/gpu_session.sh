@@ -1,23 +1,22 @@
 #!/bin/bash
-P=${1:-r02_s40}
+# final captures of the round: every profiled command first runs plain in the same call
+P=${1:-r02_final}
 O=gpurun_out
 mkdir -p $O
-python - <<PY 2>&1 | tee -a $O/${P}_c2full_refill.log
-import sys, os
-sys.path.insert(0, os.getcwd())
-import numpy as np, torch
-import cyrk_b200 as c, bench
-w = bench.WORKLOADS["C2full"]; B = 1 << 21
-y0, args = bench.make_inputs(w, B, 100)
-y0d, ad = torch.from_numpy(y0).cuda(), torch.from_numpy(args).cuda()
-kw = bench.solve_kwargs(c, w, 0)
-for prep, refill in ((-1, 0), (0, 1), (0, 2), (0, 4), (0, 8), (1, 4), (1, 1)):
-    c.lib().cyrk_b200_set_option(b"prep", prep); c.lib().cyrk_b200_set_option(b"refill_min", refill)
-    res = None; best = 1e9
-    for _ in range(3):
-        res = c.cysolve_ivp_batch(w["rhs"], (0.0, 10.0), y0d, args=ad, solution_reuse=res, **kw)
-        best = min(best, res.kernel_ms)
-    print(f"prep={prep} refill_min={refill} C2full B={B} kernel_ms={best:.3f} launches={res.launches}", flush=True)
-    res.close()
-PY
-timeout 900 python -m pytest tests/test_gpu_streaming.py tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -2
+python scripts/prof_c5.py > $O/${P}_plain_c5.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:rk_thread_kernel -s 1 -c 1 -f -o $O/${P}_prof_c5 python scripts/prof_c5.py > $O/${P}_ncu_c5.log 2>&1
+echo "c5 rc=$?"
+python scripts/ncu_kernel_summary.py $O/${P}_prof_c5.ncu-rep > $O/${P}_ncu_c5_summary.txt 2>&1; head -24 $O/${P}_ncu_c5_summary.txt
+python bench.py --steps 2 --warmup 1 --no-extras --no-cpu-baseline > $O/${P}_plain_bench.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${P}_ncu_launches_C5.csv python bench.py --steps 2 --warmup 1 --no-extras --no-cpu-baseline > $O/${P}_ncu_bench.log 2>&1
+echo "launches rc=$?"
+QB=1048576 python scripts/prof_c3full.py > $O/${P}_plain_c3.log 2>&1 &&
+QB=1048576 ncu --set full --clock-control none --import-source on -k regex:"cyrk_user_kernel|event_roots" -c 2 -f -o $O/${P}_prof_c3full python scripts/prof_c3full.py > $O/${P}_ncu_c3.log 2>&1
+echo "c3 rc=$?"
+python scripts/ncu_kernel_summary.py $O/${P}_prof_c3full.ncu-rep cyrk_user_kernel > $O/${P}_ncu_c3full_evdetect.txt 2>&1; head -24 $O/${P}_ncu_c3full_evdetect.txt
+python scripts/prof_c2tp.py 2 > $O/${P}_plain_c2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"step_dense|rk_thread_kernel" -s 2 -c 2 -f -o $O/${P}_prof_c2full python scripts/prof_c2tp.py 2 > $O/${P}_ncu_c2.log 2>&1
+echo "c2 rc=$?"
+python scripts/ncu_kernel_summary.py $O/${P}_prof_c2full.ncu-rep step_dense > $O/${P}_ncu_c2_step_dense.txt 2>&1
+python scripts/ncu_kernel_summary.py $O/${P}_prof_c2full.ncu-rep rk_thread_kernel > $O/${P}_ncu_c2_steps_solve.txt 2>&1
+ls -la $O/${P}*.ncu-rep
