@@ -175,9 +175,11 @@ struct ProbPendulum {           // cysolver_test.pyx:122-141, Performance/pendul
         const double* p = reinterpret_cast<const double*>(args);
         const double coeff_1 = p[5], coeff_2 = p[6];
         const double y0 = y[0], y1 = y[1];
-        const double torque = 0.1 * CYRK_FP_NS::psin(t);
+        double st, sy;
+        CYRK_FP_NS::psin2(t, y0, st, sy);
+        const double torque = 0.1 * st;
         dy[0] = y1;
-        dy[1] = coeff_1 * CYRK_FP_NS::psin(y0) + coeff_2 * torque;
+        dy[1] = coeff_1 * sy + coeff_2 * torque;
     }
 };
 
@@ -237,9 +239,11 @@ struct ProbPendulumDrag {       // Documentation/Advanced_CySolver.md:127-152; a
         const double c = p[3];
         const double coeff_1 = p[5], coeff_2 = p[6];
         const double y0 = y[0], y1 = y[1];
-        const double torque = 0.1 * CYRK_FP_NS::psin(t);
+        double st, sy;
+        CYRK_FP_NS::psin2(t, y0, st, sy);
+        const double torque = 0.1 * st;
         dy[0] = y1;
-        double d1 = coeff_1 * CYRK_FP_NS::psin(y0) + coeff_2 * torque;
+        double d1 = coeff_1 * sy + coeff_2 * torque;
         d1 -= c * y1;
         dy[1] = d1;
         dy[2] = torque;
