@@ -1,17 +1,23 @@
 // cta2_core.cuh -- adaptive explicit Runge-Kutta solver for LARGE systems, one CTA per trajectory,
-// REGISTER-RESIDENT variant (n_y <= C * blockDim.x, C in {1,2,4,8}, i.e. up to 4096 components at 512 threads).
+// REGISTER-RESIDENT variant: n_y <= 512 * C components, C in {1, 2, 4, 8} with every working vector on chip
+// (n_y <= 4096), C in {12, 16, 20, 24} with the stage derivatives in an L2-resident slab (n_y <= 12 288; the reference's
+// own largey has 10 000).  cta_core_params.h holds the placement of every vector as a function of (method, C).
 //
 // The first CTA kernel (cta_core.cuh) keeps every working vector in shared memory / an L2 slab behind a run-time
 // address selection and brackets every loop with __syncthreads(); it measured 11.7 SM-cycles per component-attempt
-// on BASELINE config 4 (largey, n_y = 4096, RK45) against an FP64-pipe bound of ~4.5.  Here instead
-//   * thread t OWNS the components i = t + c*blockDim.x, c < C, for the whole trajectory: y_old and the most
-//     frequently read stage derivatives K_0..K_{NREG-1} of those components live in REGISTERS, the next NSM
-//     derivatives in shared memory, only the remainder (DOP853) in a per-CTA L2-resident slab -- all placements are
-//     compile-time, so every access is a plain register / LDS / LDG with a constant offset;
+// on BASELINE config 4 (largey, n_y = 4096, RK45) against an FP64-pipe bound of ~4.5; this kernel measures 4.5 with the
+// pipe 55 % busy (profiles/r02_notes.md, section 7).  Here
+//   * thread t OWNS the components i = t + 512*c, c < C, for the whole trajectory (C = 1: one thread per component):
+//     y_old and the most frequently read stage derivatives K_0..K_{NREG-1} of those components live in REGISTERS, the
+//     next NSM derivatives in shared memory, the remainder in a per-CTA L2-resident slab -- placements, strides and
+//     vector lengths are compile-time and the solver holds ONE shared-memory base pointer, so every access is a plain
+//     register / LDS / LDG with a constant offset;
 //   * the only data other threads ever read is the stage INPUT vector (the right-hand side may couple components),
 //     which is double-buffered in shared memory: ONE __syncthreads() per right-hand-side evaluation, plus one for
 //     the (double-buffered) error-norm reduction -- 7 barriers per RK45 attempt instead of 16;
-//   * the problem's auxiliary table (largey: the per-component rates) sits in shared memory as well;
+//   * the right-hand side is inlined into a rolled loop over the thread's components (one copy of its code per stage)
+//     whose results pass through the thread's own slots of a memory vector -- see eval_into / eval_rhs;
+//   * the problem's auxiliary table (largey: the per-component rates) sits in shared memory as well (slab from C = 20);
 //   * every step-size decision comes from a CTA-wide reduction, so all threads take the same branch;
 //   * accepted rows are streamed to HBM straight from the owning threads, one coalesced row per step.
 //
@@ -23,8 +29,9 @@
 // Stored dense output: one coalesced record [y_old | Q_0 | .. | Q_{QO-1}] per accepted step, evaluated afterwards by
 // cta_dense_eval_kernel.  Events: the values g_e(t, y) are evaluated by thread 0 on the complete vector and published
 // through shared memory; every thread then runs the reference's trigger logic and Brent iteration redundantly (identical
-// inputs -> identical branches), interpolating its own components of the state for each evaluation.  Not available on
-// this path (the host shim rejects it): extra outputs.
+// inputs -> identical branches), interpolating its own components of the state for each evaluation.  Extra outputs
+// (problems that declare HAS_EXTRAS): the functor's components n_y .., evaluated at every saved row; not together with
+// t_eval, events or a dense store (the host shim says so).
 #pragma once
 
 #ifndef CYRK_EVAL_WIDTH
