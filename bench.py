@@ -23,6 +23,7 @@ Printed JSON line (rank 0):
             trajectories whose (accepted, rejected, rows, nfev) agree, largest error in units of the
             10*rtol*|y| + 10*atol tolerance.  The run FAILS (exit 2) when a step-sequence agreement is below 0.999.
   workloads (N=1) the other BASELINE configs timed the same way, 3 steps each: value, e2e, roofline fraction, bound
+  config.size_sweep       (N=1) the headline workload at 16 / 32 / 64 Mi trajectories on one GPU (two steps each)
   config.strong_scaling   (N>1) a fixed 8 Mi-trajectory job split over the N GPUs (the weak-scaling headline keeps
             8 Mi per GPU); config.ensemble: the optional NCCL ensemble reduction, checked against numpy on rank 0
 
@@ -523,6 +524,20 @@ def main():
                   "value": steps * total / (s_dev * 1e-3), "ms_per_step": s_dev / steps,
                   "e2e_value": steps * total / (s_e2e * 1e-3), "e2e_ms_per_step": s_e2e / steps}
 
+    # ---- size sweep of the headline workload on one GPU (C5 = the C1 generator at 8, 16, 32, 64 Mi trajectories)
+    sweep = None
+    if dist is None and not a.no_extras and a.workload == "C5":
+        sweep = {}
+        for mi in (16, 32, 64):
+            _log(f"size sweep: {mi} Mi trajectories")
+            nb = mi * 1024 * 1024
+            ms = gpu_measure(c, torch, w, nb, 100 + int(np.log2(mi // 8)), local_rank, 2, 3, barrier)
+            ms.pop("result").close()
+            sweep[f"{mi}Mi"] = {"value": 2 * nb / (ms["dev_ms"] * 1e-3), "ms_per_step": ms["dev_ms"] / 2,
+                                "e2e": 2 * nb / (ms["e2e_wall_ms"] * 1e-3), "e2e_ms_per_step": ms["e2e_wall_ms"] / 2,
+                                "all_success": bool(ms["ok"])}
+            torch.cuda.empty_cache()
+
     # ---- max over ranks
     dev_ms, ker_ms, e2e_wall_ms, wall_ms = max_over_ranks([m["dev_ms"], m["ker_ms"], m["e2e_wall_ms"], m["wall_ms"]])
     cnt = torch.tensor([m["attempts"], m["steps_acc"], m["launches"] + m["e2e_launches"] * steps, int(m["ok"])], dtype=torch.int64, device=dev)
@@ -567,6 +582,8 @@ def main():
         }
         if strong:
             line["config"]["strong_scaling"] = strong
+        if sweep:
+            line["config"]["size_sweep"] = sweep
         if ensemble:
             line["config"]["ensemble"] = ensemble
         if world == 1 and not a.no_cpu_baseline:
