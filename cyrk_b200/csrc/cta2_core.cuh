@@ -40,6 +40,9 @@
 #ifndef CYRK_EVAL_UNROLL
 #define CYRK_EVAL_UNROLL 8     // unroll factor of the per-thread component loop of a right-hand-side evaluation
 #endif
+#ifndef CYRK_EVAL_UNROLL_LARGE
+#define CYRK_EVAL_UNROLL_LARGE 4     // the same for C >= 12 (stage derivatives in the slab)
+#endif
 #include "rk_core.cuh"
 #include "cta_core_params.h"
 
@@ -195,7 +198,10 @@ struct Cta2Solver {
     // Slots past n_y (the CTA's padding) evaluate component n_y - 1: no branch, and nobody reads those slots.
     CYRK_DI void eval_into(double* dst, double t, const double* in) const
     {
-        constexpr int UNR = CYRK_EVAL_UNROLL < C ? CYRK_EVAL_UNROLL : C;
+        // (slab-resident range, C >= 12: unrolled 4 times -- n_y = 10 000: 18.1 ms against 19.3 with 8 and 29.7 fully
+        // unrolled, profiles/r02_ab_c4ref_unroll.log)
+        constexpr int UNR_CFG = C >= 12 ? CYRK_EVAL_UNROLL_LARGE : CYRK_EVAL_UNROLL;
+        constexpr int UNR = UNR_CFG < C ? UNR_CFG : C;
         const unsigned last = n - 1u;
         if constexpr (HasTprep<Prob>::value) {
             auto u = Prob::tprep(t, args);

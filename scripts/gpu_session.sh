@@ -1,7 +1,5 @@
 #!/bin/bash
-P=${1:-r02_s47}
+P=${1:-r02_s49}
 O=gpurun_out
 mkdir -p $O
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/${P}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/${P}_smoke.log
-timeout 1800 python -m pytest tests -m gpu -q -x > $O/${P}_gpu_tests.log 2>&1
-tail -3 $O/${P}_gpu_tests.log
+for n in 10000 8192 6000 12288; do QN=$n QB=2048 python scripts/ab_variants.py scripts/quick_c4.py 2>&1 | grep -v "largey_simple\|RK23" ; done | tee $O/${P}_large_unroll.log
