@@ -1261,6 +1261,7 @@ static int solve_thread_path(Handle* h, const SolveArgs& a, const Dispatch* pe)
 // Returns 0, -1, or 2 = "not streamable after all" (the caller falls back to the single-arena path).
 // ------------------------------------------------------------------------------------------------
 static int g_opt_stream_chunk = 0;       // trajectories per chunk (0 = by arena size)
+static int g_opt_stream_taper = 1;       // two automatic halves become chunks of 1/2, 1/3, 1/6 (see solve_thread_streamed)
 static int g_opt_stream = 1;             // 0 = never stream
 
 static size_t stream_chunk_for(const SolveArgs& a, const Dispatch* pe)
@@ -1364,7 +1365,20 @@ static int solve_thread_streamed(Handle* h, const SolveArgs& a, const Dispatch* 
 
     size_t row_cap = 0, scap = 0;
     bool planned = false, use_recs = false;
-    const size_t nchunk = (B + chunk - 1) / chunk;
+    // Chunk schedule.  Equal chunks in general; when the automatic rule settled on two halves (memory is not the limit),
+    // three chunks of 1/2, 1/3 and 1/6 of the batch instead: the copy-out of the LAST chunk is the part no solve overlaps,
+    // every chunk costs one drain phase, and a chunk's copy-out has to fit under the next chunk's solve (C3full, 4 Mi:
+    // kernels 61.3 ms in one launch + ~2.7 ms per further chunk; 33 ms of copy-out in total; profiles/r02_notes.md)
+    std::vector<std::pair<size_t, size_t>> sched;          // (offset, count)
+    if (g_opt_stream_chunk <= 0 && g_opt_stream_taper && chunk < B && B <= 2 * chunk && B >= 6 * 16384) {
+        const size_t n0 = (B / 2 + 1023) / 1024 * 1024, n1 = (B / 3 + 1023) / 1024 * 1024;
+        sched.emplace_back(0, n0);
+        sched.emplace_back(n0, n1);
+        sched.emplace_back(n0 + n1, B - n0 - n1);
+    } else {
+        for (size_t off = 0; off < B; off += chunk) sched.emplace_back(off, std::min(chunk, B - off));
+    }
+    const size_t nchunk = sched.size();
     for (int plan = 0;; plan++) {
         if (plan >= 8) { set_error("streamed solve: capacity re-planning did not converge"); return -1; }
         bool replan = false;
@@ -1375,7 +1389,7 @@ static int solve_thread_streamed(Handle* h, const SolveArgs& a, const Dispatch* 
             if (use_recs && h->d_st.ensure(B * scap * RA * 8)) return -1;
         }
         for (size_t c = 0; c < nchunk && !replan; c++) {
-            const size_t off = c * chunk, n = std::min(chunk, B - off);
+            const size_t off = sched[c].first, n = sched[c].second;
             Handle* s = h->sub[c & 1];
             SolveArgs ac = a;
             ac.n_traj = n;
@@ -2278,6 +2292,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "dense_store")) { g_opt_dense_store = value; return 0; }
     if (!strcmp(name, "stream")) { g_opt_stream = value; return 0; }
     if (!strcmp(name, "stream_chunk")) { g_opt_stream_chunk = value; return 0; }
+    if (!strcmp(name, "stream_taper")) { g_opt_stream_taper = value; return 0; }
     if (!strcmp(name, "shared_args")) { g_opt_shared_args = value; return 0; }
     if (!strcmp(name, "events_variant")) { g_opt_events_variant = value; return 0; }
     if (!strcmp(name, "events_two_pass")) { g_opt_events_two_pass = value; return 0; }

@@ -1,5 +1,7 @@
 #!/bin/bash
-P=${1:-r02_s49}
+P=${1:-r02_s50}
 O=gpurun_out
 mkdir -p $O
-for n in 10000 8192 6000 12288; do QN=$n QB=2048 python scripts/ab_variants.py scripts/quick_c4.py 2>&1 | grep -v "largey_simple\|RK23" ; done | tee $O/${P}_large_unroll.log
+python scripts/quick_c3full_e2e.py 2>&1 | tee $O/${P}_c3full_e2e_taper.log
+timeout 900 python -m pytest tests/test_gpu_streaming.py -m gpu -q -x 2>&1 | tail -2
+python scripts/check_streaming_full.py 2>&1 | grep "equal\|call 1" | tee $O/${P}_streaming_full.log
