@@ -1317,16 +1317,46 @@ static int solve_thread_streamed(Handle* h, const SolveArgs& a, const Dispatch* 
     auto sync_subs = [&]() -> int {
         CU_TRY(cudaStreamSynchronize(h->sub[0]->stream));
         CU_TRY(cudaStreamSynchronize(h->sub[1]->stream));
+        CU_TRY(cudaStreamSynchronize(h->s_h2d));          // (the copy-in of the later chunks' inputs: the caller owns that memory)
         return 0;
     };
     CU_TRY(cudaEventRecord(h->ev_begin, h->stream));
 
-    // ---- whole-batch inputs, uploaded once; the chunk solves read them in place
-    if (upload(h, h->d_y0, a.y0, B * NY * 8)) return -1;
+    // Chunk schedule.  Equal chunks in general; when the automatic rule settled on two halves (memory is not the limit),
+    // three chunks of 1/2, 1/3 and 1/6 of the batch instead: the copy-out of the LAST chunk is the part no solve overlaps,
+    // every chunk costs one drain phase, and a chunk's copy-out has to fit under the next chunk's solve (C3full, 4 Mi:
+    // kernels 61.3 ms in one launch + ~2.7 ms per further chunk; 33 ms of copy-out in total; profiles/r02_notes.md)
+    std::vector<std::pair<size_t, size_t>> sched;          // (offset, count)
+    if (g_opt_stream_chunk <= 0 && g_opt_stream_taper && chunk < B && B <= 2 * chunk && B >= 6 * 16384) {
+        const size_t n0 = (B / 2 + 1023) / 1024 * 1024, n1 = (B / 3 + 1023) / 1024 * 1024;
+        sched.emplace_back(0, n0);
+        sched.emplace_back(n0, n1);
+        sched.emplace_back(n0 + n1, B - n0 - n1);
+    } else {
+        for (size_t off = 0; off < B; off += chunk) sched.emplace_back(off, std::min(chunk, B - off));
+    }
+    const size_t nchunk = sched.size();
+
+    // ---- whole-batch inputs, uploaded once; the chunk solves read them in place.  Only the FIRST chunk's share is waited
+    // for: the rest goes through the copy-in stream while the first chunk is solved (later chunks wait on `ev_rest`).
+    const size_t n_first = sched[0].second;
+    if (h->events(1)) return -1;
+    cudaEvent_t ev_rest = h->ev_pool[0];
+    if (h->d_y0.ensure(B * NY * 8)) return -1;
+    CU_TRY(cudaMemcpyAsync(h->d_y0.p, a.y0, n_first * NY * 8, cudaMemcpyHostToDevice, h->stream));
+    if (B > n_first)
+        CU_TRY(cudaMemcpyAsync(h->d_y0.as<double>() + n_first * NY, a.y0 + n_first * NY, (B - n_first) * NY * 8, cudaMemcpyHostToDevice, h->s_h2d));
+    h->h2d_bytes += B * NY * 8;
     if (pe->nargs_dbl > 0) {
         const size_t n_blobs = per_args ? B : 1;
         if (a.args_len == args_stride && a.n_args >= 1) {
-            if (upload(h, h->d_args, a.args, n_blobs * args_stride)) return -1;
+            if (h->d_args.ensure(n_blobs * args_stride)) return -1;
+            const size_t nb_first = per_args ? n_first : 1;
+            CU_TRY(cudaMemcpyAsync(h->d_args.p, a.args, nb_first * args_stride, cudaMemcpyHostToDevice, h->stream));
+            if (n_blobs > nb_first)
+                CU_TRY(cudaMemcpyAsync(h->d_args.as<char>() + nb_first * args_stride, a.args + nb_first * args_stride,
+                                       (n_blobs - nb_first) * args_stride, cudaMemcpyHostToDevice, h->s_h2d));
+            h->h2d_bytes += n_blobs * args_stride;
         } else {                                                    // zero-pad every blob to the functor's size
             if (h->h_stage.ensure(n_blobs * args_stride)) return -1;
             char* st = h->h_stage.as<char>();
@@ -1337,6 +1367,7 @@ static int solve_thread_streamed(Handle* h, const SolveArgs& a, const Dispatch* 
         }
     } else if (h->d_args.ensure(8)) return -1;
     if (upload(h, h->d_tspan, a.t_span, a.n_t_span * 16)) return -1;
+    CU_TRY(cudaEventRecord(ev_rest, h->s_h2d));
     CU_TRY(cudaStreamSynchronize(h->stream));
     h->in_y0 = h->d_y0.as<double>(); h->in_args = h->d_args.as<char>(); h->in_tspan = h->d_tspan.as<double>();
     h->tspan_stride = per_span ? 2u : 0u; h->args_stride = per_args ? args_stride : 0;
@@ -1365,20 +1396,6 @@ static int solve_thread_streamed(Handle* h, const SolveArgs& a, const Dispatch* 
 
     size_t row_cap = 0, scap = 0;
     bool planned = false, use_recs = false;
-    // Chunk schedule.  Equal chunks in general; when the automatic rule settled on two halves (memory is not the limit),
-    // three chunks of 1/2, 1/3 and 1/6 of the batch instead: the copy-out of the LAST chunk is the part no solve overlaps,
-    // every chunk costs one drain phase, and a chunk's copy-out has to fit under the next chunk's solve (C3full, 4 Mi:
-    // kernels 61.3 ms in one launch + ~2.7 ms per further chunk; 33 ms of copy-out in total; profiles/r02_notes.md)
-    std::vector<std::pair<size_t, size_t>> sched;          // (offset, count)
-    if (g_opt_stream_chunk <= 0 && g_opt_stream_taper && chunk < B && B <= 2 * chunk && B >= 6 * 16384) {
-        const size_t n0 = (B / 2 + 1023) / 1024 * 1024, n1 = (B / 3 + 1023) / 1024 * 1024;
-        sched.emplace_back(0, n0);
-        sched.emplace_back(n0, n1);
-        sched.emplace_back(n0 + n1, B - n0 - n1);
-    } else {
-        for (size_t off = 0; off < B; off += chunk) sched.emplace_back(off, std::min(chunk, B - off));
-    }
-    const size_t nchunk = sched.size();
     for (int plan = 0;; plan++) {
         if (plan >= 8) { set_error("streamed solve: capacity re-planning did not converge"); return -1; }
         bool replan = false;
@@ -1402,6 +1419,7 @@ static int solve_thread_streamed(Handle* h, const SolveArgs& a, const Dispatch* 
             ac.flags |= CYRK_FLAG_DEVICE_IO;
             if (a.flags & CYRK_FLAG_TOL_PER_TRAJ) { ac.rtols = a.rtols + off * NY; ac.atols = a.atols + off * NY; ac.n_rtols = ac.n_atols = n * NY; }
             if (a.n_t_eval && (a.flags & CYRK_FLAG_T_EVAL_PER_TRAJ)) ac.t_eval = a.t_eval + off * a.n_t_eval;
+            if (c > 0) CU_TRY(cudaStreamWaitEvent(s->stream, ev_rest, 0));      // (the inputs beyond the first chunk)
             s->force = Handle::Force();
             s->force.active = true;
             s->force.ev_base = ev_base;
