@@ -96,7 +96,8 @@ static int g_opt_cta2_large = 1;      // register-resident CTA kernel for 4096 <
 static int g_opt_cta_smem_vecs = -1;  // CTA path: working vectors kept in shared memory (-1 = as many as fit)
 static int g_opt_cta_block = 0;       // CTA path: threads per CTA (0 = by n_y)
 static int g_opt_pipe_taper = 1;       // pipelined host-I/O path: short first / last chunks
-static int g_opt_pipe_chunk = 1 << 20; // pipelined host-I/O path: trajectories per chunk (at most 32 chunks)
+static int g_opt_pipe_chunk = 1 << 21; // pipelined host-I/O path: trajectories per chunk (at most 32 chunks, at least 4).  2 Mi since the start-up
+                                       // kernel runs from 256 Ki: 8 Mi LV trajectories end to end 19.33 ms against 20.02 with 1 Mi (profiles/r02_e2e_pipe_chunk.log)
 static int g_opt_pipe_min = 1 << 18;   // pipelined host-I/O path: smallest batch that takes it (0 = never)
 static int g_opt_cta_kernel = 0;      // CTA path: 0 = pick (register-resident kernel where it is faster), 1 = always the
                                       // shared-memory/slab kernel, 2 = the register-resident kernel whenever n_y <= 4096
@@ -468,7 +469,7 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
     const size_t args_stride = (size_t)pe->nargs_dbl * sizeof(double);
     // Chunk schedule: full chunks in the middle, a short one in front (the first copy-in is not overlapped with any
     // compute) and two short ones at the end (the last copy-out is not overlapped either).
-    // chunk size: `pipe_chunk` (1 Mi: measured best at 8 Mi) for large batches, a quarter of the batch below 4 Mi so that
+    // chunk size: `pipe_chunk` (2 Mi: measured best at 8 Mi) for large batches, a quarter of the batch below 4 Mi so that
     // a 256 Ki ... 2 Mi batch still overlaps its copies with the solve; never more than 32 chunks
     const size_t chunk = std::max<size_t>(std::min<size_t>((size_t)g_opt_pipe_chunk, ((B + 3) / 4 + 1023) / 1024 * 1024), (B + 31) / 32);
     std::vector<std::pair<size_t, size_t>> sched;          // (offset, count)

@@ -33,4 +33,4 @@ for B in (1 << 18, 1 << 20, 1 << 21, 1 << 23):
         print(f"  B={B} pipe_min={pmin} chunk={chunk} taper={taper}: wall_ms mean={tot / n:.3f} best={best:.3f} device_total_ms={res.total_ms:.3f} "
               f"launches={res.launches} d2h={res.d2h_bytes} -> {B / (tot / n) * 1e3:.3e} solves/s ({dev_ms / (tot / n):.2f} of device-resident)", flush=True)
         res.close()
-    L.cyrk_b200_set_option(b"pipe_min", 1 << 18); L.cyrk_b200_set_option(b"pipe_chunk", 1 << 20); L.cyrk_b200_set_option(b"pipe_taper", 1)
+    L.cyrk_b200_set_option(b"pipe_min", 1 << 18); L.cyrk_b200_set_option(b"pipe_chunk", 1 << 21); L.cyrk_b200_set_option(b"pipe_taper", 1)

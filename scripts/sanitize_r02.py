@@ -37,7 +37,7 @@ r = c.cysolve_ivp_batch("lotkavolterra", (0, 3), y0, method="RK45", args=[1.5, 1
 L.cyrk_b200_set_option(b"pipe_min", 256); L.cyrk_b200_set_option(b"pipe_chunk", 1024)
 r = c.cysolve_ivp_batch("lotkavolterra", (0, 3), y0, method="DOP853", args=[1.5, 1, 3, 1], rtol=rt, atol=at, store="final")
 _ = np.array(r.n_rejected), np.array(r.t_last)
-L.cyrk_b200_set_option(b"pipe_min", 1 << 18); L.cyrk_b200_set_option(b"pipe_chunk", 1 << 20)
+L.cyrk_b200_set_option(b"pipe_min", 1 << 18); L.cyrk_b200_set_option(b"pipe_chunk", 1 << 21)
 # extra outputs on the CTA path (register-resident and slab kernels)
 from test_user_rhs import CHAIN_X_SRC
 u = c.UserRHS(CHAIN_X_SRC, "chainx", n_y=0, n_extra=2, args_bytes=8)
