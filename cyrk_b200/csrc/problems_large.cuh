@@ -49,13 +49,14 @@ struct ProbLargeY {
                                                    unsigned& slow, double (&out)[W])
     {
         const double MAGIC = 6755399441055744.0;
-        double x[W], qd[W], r[W], z[W], p[W], amp[W];
+        double x[W], qd[W], r[W], z[W], p[W], rate[W], yi[W];
         int q[W];
 #pragma unroll
         for (int w = 0; w < W; w++) {
             const double yn = (i[w] < (n - 1)) ? y[i[w] + 1] : 0.0;
             x[w] = fma(yn, 0.02, ph);
-            amp[w] = aux[i[w]] * y[i[w]];
+            rate[w] = aux[i[w]];           // (loaded here, used after the polynomial: from C = 20 on aux lives in the L2 slab)
+            yi[w] = y[i[w]];
         }
 #pragma unroll
         for (int w = 0; w < W; w++) slow = max(slow, (unsigned)__double2hiint(x[w]) & 0x7fffffffu);
@@ -81,7 +82,7 @@ struct ProbLargeY {
 #pragma unroll
         for (int w = 0; w < W; w++) {
             const double res = fma(z[w], p[w], r[w]);
-            out[w] = amp[w] * __hiloint2double(__double2hiint(res) ^ (q[w] << 31), __double2loint(res));
+            out[w] = rate[w] * yi[w] * __hiloint2double(__double2hiint(res) ^ (q[w] << 31), __double2loint(res));
         }
     }
 #endif
