@@ -19,7 +19,7 @@ Printed JSON line (rank 0):
             to it to show the path is not bandwidth bound
   cpu_baseline   the reference's own CPU path (oracle/_ref when present, else the C port) on a bounded sample
   parity    (N=1) the GPU path against that same CPU reference on the SAME sample -- >= 1 Mi trajectories for the
-            headline workload, 64 Ki for C2 / C3, 64 for C4 -- in both FP builds: status equality, share of
+            headline workload, 128 Ki for C2 / C3, 512 for C4 (128 at n_y = 10 000) -- in both FP builds: status equality, share of
             trajectories whose (accepted, rejected, rows, nfev) agree, largest error in units of the
             10*rtol*|y| + 10*atol tolerance.  The run FAILS (exit 2) when a step-sequence agreement is below 0.999.
   workloads (N=1) the other BASELINE configs timed the same way, 3 steps each: value, e2e, roofline fraction, bound
@@ -116,7 +116,7 @@ def full_batch(name):
             b //= 2
     return b
 # parity samples next to the headline one: workload -> trajectories
-PARITY_SAMPLES = {"C2full": 64 * 1024, "C3full": 64 * 1024, "C4": 64, "C4ref": 16}
+PARITY_SAMPLES = {"C2full": 128 * 1024, "C3full": 128 * 1024, "C4": 512, "C4ref": 128}
 
 
 def make_inputs(w, n, seed):
