@@ -177,7 +177,7 @@ struct ProbPendulum {           // cysolver_test.pyx:122-141, Performance/pendul
         const double y0 = y[0], y1 = y[1];
         double st, sy;
         CYRK_FP_NS::psin2(t, y0, st, sy);
-        const double torque = 0.1 * st;
+        const double torque = CYRK_LIT_TENTH * st;
         dy[0] = y1;
         dy[1] = coeff_1 * sy + coeff_2 * torque;
     }
@@ -241,7 +241,7 @@ struct ProbPendulumDrag {       // Documentation/Advanced_CySolver.md:127-152; a
         const double y0 = y[0], y1 = y[1];
         double st, sy;
         CYRK_FP_NS::psin2(t, y0, st, sy);
-        const double torque = 0.1 * st;
+        const double torque = CYRK_LIT_TENTH * st;
         dy[0] = y1;
         double d1 = coeff_1 * sy + coeff_2 * torque;
         d1 -= c * y1;

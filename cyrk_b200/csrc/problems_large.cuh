@@ -48,7 +48,7 @@ struct ProbLargeY {
     __device__ __forceinline__ static void eval_uw(const unsigned (&i)[W], double ph, const double* y, unsigned n, const char*, const double* aux,
                                                    unsigned& slow, double (&out)[W])
     {
-        const double MAGIC = 6755399441055744.0;
+        const double MAGIC = CYRK_FP_NS::g_sinpi.r[4];
         double x[W], qd[W], r[W], z[W], p[W], rate[W], yi[W];
         int q[W];
 #pragma unroll
@@ -61,15 +61,15 @@ struct ProbLargeY {
 #pragma unroll
         for (int w = 0; w < W; w++) slow = max(slow, (unsigned)__double2hiint(x[w]) & 0x7fffffffu);
 #pragma unroll
-        for (int w = 0; w < W; w++) qd[w] = fma(x[w], 0.3183098861837907, MAGIC);
+        for (int w = 0; w < W; w++) qd[w] = fma(x[w], CYRK_FP_NS::g_sinpi.r[0], MAGIC);
 #pragma unroll
         for (int w = 0; w < W; w++) { q[w] = __double2loint(qd[w]); qd[w] -= MAGIC; }
 #pragma unroll
-        for (int w = 0; w < W; w++) r[w] = fma(qd[w], -3.141592653589793, x[w]);
+        for (int w = 0; w < W; w++) r[w] = fma(qd[w], CYRK_FP_NS::g_sinpi.r[1], x[w]);
 #pragma unroll
-        for (int w = 0; w < W; w++) r[w] = fma(qd[w], -1.2246467991473532e-16, r[w]);
+        for (int w = 0; w < W; w++) r[w] = fma(qd[w], CYRK_FP_NS::g_sinpi.r[2], r[w]);
 #pragma unroll
-        for (int w = 0; w < W; w++) r[w] = fma(qd[w], 2.9947698097183397e-33, r[w]);
+        for (int w = 0; w < W; w++) r[w] = fma(qd[w], CYRK_FP_NS::g_sinpi.r[3], r[w]);
 #pragma unroll
         for (int w = 0; w < W; w++) { z[w] = r[w] * r[w]; p[w] = CYRK_FP_NS::g_sinpi.c[7]; }
 #pragma unroll

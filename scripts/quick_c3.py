@@ -13,7 +13,9 @@ def run(tag, **kw):
         res = c.cysolve_ivp_batch("pendulum_drag", ts, y0, method="RK23", args=args, rtol=1e-6, atol=1e-8, num_extra=1, store="final", solution_reuse=res, **kw)
         best = min(best, res.kernel_ms)
     st = torch.as_tensor(res.steps_taken, device="cuda").sum().item(); nr = torch.as_tensor(res.n_rejected, device="cuda").sum().item()
-    print(f"{tag:40s} kernel_ms={best:8.2f} attempts/traj={(st+nr)/B:7.1f} solves/s={B/best*1e3:.3e}", flush=True)
+    import hashlib
+    dg = hashlib.md5(torch.as_tensor(res.y_last, device="cuda").cpu().numpy().tobytes() + torch.as_tensor(res.nfev, device="cuda").cpu().numpy().tobytes()).hexdigest()[:12]
+    print(f"{tag:40s} kernel_ms={best:8.2f} attempts/traj={(st+nr)/B:7.1f} solves/s={B/best*1e3:.3e} digest={dg}", flush=True)
     res.close()
 rb = int(os.environ.get("RB", 8)); c.lib().cyrk_b200_set_option(b"root_batch", rb); print("root_batch", rb)
 run("no events (LEAN)")

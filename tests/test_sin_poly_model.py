@@ -51,13 +51,16 @@ int main(void) {
 
 def _header_constants():
     src = open(os.path.join(ROOT, "cyrk_b200", "csrc", "rk_core.cuh")).read()
-    tab = re.search(r"g_sinpi = \{\{(.*?)\}\};", src, re.S).group(1)
+    # g_sinpi = {{ c[0..7] }, { 1/pi, -pi (three pieces), magic }}: polynomial and reduction constants live in one table
+    m = re.search(r"g_sinpi = \{\{(.*?)\},\s*\{(.*?)\}\};", src, re.S)
+    tab, red = m.group(1), [x.strip() for x in m.group(2).split(",")]
+    assert len(red) == 5 and float(red[4]) == 6755399441055744.0
     body = src[src.index("CYRK_DI double psin_pi(double x)"):]
     body = body[:body.index("\n}\n")]
-    inv_pi = re.search(r"fma\(x, ([0-9.eE+-]+), MAGIC\)", body).group(1)
-    steps = re.findall(r"r = fma\(qd, ([0-9.eE+-]+), (?:x|r)\);", body)
-    assert len(steps) == 3
-    return dict(coefs=" ".join(tab.split()), inv_pi=inv_pi, pi_hi=steps[0], pi_mid=steps[1], pi_lo=steps[2])
+    # the function uses the table entries in this order
+    assert "fma(x, g_sinpi.r[0], MAGIC)" in body and "fma(qd, g_sinpi.r[1], x)" in body
+    assert "fma(qd, g_sinpi.r[2], r)" in body and "fma(qd, g_sinpi.r[3], r)" in body
+    return dict(coefs=" ".join(tab.split()), inv_pi=red[0], pi_hi=red[1], pi_mid=red[2], pi_lo=red[3])
 
 
 def test_psin_pi_model_within_two_ulp(tmp_path):
