@@ -1510,7 +1510,8 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         if (a.rhs_id < CYRK_RHS_USER_BASE) { set_error("the built-in large problems have no extra outputs"); return -1; }
         if (a.n_t_eval || a.n_events || a.dense_output) { set_error("extra outputs on the CTA-per-trajectory path: raw step rows / final state only (no t_eval, events or dense_output)"); return -1; }
     }
-    if (a.flags & (CYRK_FLAG_T_EVAL_PER_TRAJ | CYRK_FLAG_TOL_PER_TRAJ)) { set_error("per-trajectory t_eval / tolerances are available on the thread-per-trajectory path (n_y <= 32) only"); return -1; }
+    const bool tol_pt = (a.flags & CYRK_FLAG_TOL_PER_TRAJ) != 0;                       // rtols / atols: [n_traj][n_y]
+    const bool te_pt = a.n_t_eval > 0 && (a.flags & CYRK_FLAG_T_EVAL_PER_TRAJ) != 0;   // t_eval: [n_traj][n_t_eval]
     const bool dense = a.dense_output != 0;
     const bool user_rhs = a.rhs_id >= CYRK_RHS_USER_BASE;
     if (!user_rhs && (a.n_args == 0 || a.args_len < 8)) { set_error("largey problems need args = (decay_rate, ...)"); return -1; }
@@ -1538,20 +1539,23 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
         p.max_num_steps = (unsigned)std::min<size_t>(mx, 0xffffffffu);
     }
     CU_TRY(cudaEventRecord(h->ev_begin, h->stream));
-    // tolerances, expanded to n_y entries
-    std::vector<double> rt(N), at(N);
-    for (size_t i = 0; i < N; i++) {
-        double r = a.rtols[a.n_rtols > 1 ? i : 0];
+    // tolerances, expanded to n_y entries (one row, or with CYRK_FLAG_TOL_PER_TRAJ one row per trajectory); rtol floored
+    // like the reference does in place (rk.cpp:600-608)
+    const size_t n_tol = tol_pt ? B * N : N;
+    std::vector<double> rt(n_tol), at(n_tol);
+    for (size_t i = 0; i < n_tol; i++) {
+        double r = tol_pt ? a.rtols[i] : a.rtols[a.n_rtols > 1 ? i : 0];
         if (r < 100.0 * std::numeric_limits<double>::epsilon()) r = 100.0 * std::numeric_limits<double>::epsilon();
         rt[i] = r;
-        at[i] = a.atols[a.n_atols > 1 ? i : 0];
+        at[i] = tol_pt ? a.atols[i] : a.atols[a.n_atols > 1 ? i : 0];
     }
-    if (h->d_rtol.ensure(N * 8) || h->d_atol.ensure(N * 8)) return -1;
-    CU_TRY(cudaMemcpyAsync(h->d_rtol.p, rt.data(), N * 8, cudaMemcpyHostToDevice, h->stream));
-    CU_TRY(cudaMemcpyAsync(h->d_atol.p, at.data(), N * 8, cudaMemcpyHostToDevice, h->stream));
+    if (h->d_rtol.ensure(n_tol * 8) || h->d_atol.ensure(n_tol * 8)) return -1;
+    CU_TRY(cudaMemcpyAsync(h->d_rtol.p, rt.data(), n_tol * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->d_atol.p, at.data(), n_tol * 8, cudaMemcpyHostToDevice, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
     p.rtol = h->d_rtol.as<double>();
     p.atol = h->d_atol.as<double>();
+    p.tol_stride = tol_pt ? (unsigned)N : 0u;
     if (device_io) {
         p.y0 = a.y0; p.args = a.args; p.t_span = a.t_span;
     } else {
@@ -1565,11 +1569,16 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     h->in_y0 = p.y0; h->in_args = p.args; h->in_tspan = p.t_span; h->tspan_stride = p.t_span_stride; h->args_stride = p.args_stride;
     std::vector<double> te;
     if (a.n_t_eval) {
-        te.assign(a.t_eval, a.t_eval + a.n_t_eval);
+        const size_t n_rows = te_pt ? B : 1;
+        te.assign(a.t_eval, a.t_eval + n_rows * a.n_t_eval);
         double ts0[2];
         if (device_io) { CU_TRY(cudaMemcpy(ts0, a.t_span, 16, cudaMemcpyDeviceToHost)); }
         else { ts0[0] = a.t_span[0]; ts0[1] = a.t_span[1]; }
-        if (!((ts0[1] - ts0[0]) >= 0.0)) std::reverse(te.begin(), te.end());
+        // the kernels read an ascending table (reversed copy for backward runs, cysolver.cpp:520-527); validate() has
+        // checked that every trajectory runs in the direction of the first one
+        if (!((ts0[1] - ts0[0]) >= 0.0))
+            for (size_t r = 0; r < n_rows; r++) std::reverse(te.begin() + r * a.n_t_eval, te.begin() + (r + 1) * a.n_t_eval);
+        p.t_eval_stride = te_pt ? (unsigned)a.n_t_eval : 0u;
         if (h->d_teval.ensure(te.size() * 8)) return -1;
         CU_TRY(cudaMemcpyAsync(h->d_teval.p, te.data(), te.size() * 8, cudaMemcpyHostToDevice, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
@@ -1598,17 +1607,24 @@ static int solve_cta_path(Handle* h, const SolveArgs& a, int fp)
     // that, and for DOP853, the shared-memory/slab kernel of cta_core.cuh
     const bool cta2_slab_ok = N > (size_t)cta2_max_c_onchip * cta2_max_block && N <= (size_t)cta2_max_c * cta2_max_block &&
                               a.method != CYRK_METHOD_DOP853 && g_opt_cta2_large;
-    const bool use_cta2 = !whole_vector && g_opt_cta_kernel != 1 &&
+    // per-trajectory tolerance rows / t_eval rows: the shared-memory/slab kernel (any n_y) reads them through per-trajectory
+    // pointers; the register-capped kernel is left alone (the row offsets cost its uniform-tolerance instantiations
+    // 1.5 ... 4.7 % at n_y = 4096 even when unused, profiles/r02_notes.md)
+    const bool use_cta2 = !whole_vector && g_opt_cta_kernel != 1 && !tol_pt && !te_pt &&
                           (N <= (size_t)cta2_max_c_onchip * cta2_max_block || cta2_slab_ok);
     int cta2_C = 0;
     int block, grid;
     size_t smem;
     {
-        bool uni = true;
+        bool uni = !tol_pt;              // (per-trajectory rows are always read from the arrays)
         for (size_t i = 1; i < N && uni; i++) uni = (rt[i] == rt[0]) && (at[i] == at[0]);
         p.uniform_tol = uni ? 1 : 0;
         p.rtol0 = rt[0];
         p.atol0 = at[0];
+    }
+    if ((a.n_events || dense) && (tol_pt || te_pt)) {
+        set_error("CTA-per-trajectory path: per-trajectory t_eval / tolerances cannot be combined with events or stored dense output");
+        return -1;
     }
     if (a.n_events && !use_cta2) {
         set_error("events on the CTA-per-trajectory path need the register-resident kernel (n_y <= %d; RK23 / RK45: n_y <= %d)",

@@ -72,6 +72,7 @@ struct CtaSolver {
     double* red;
     unsigned n;
     const char* args;
+    const double *rtolp, *atolp;          // this trajectory's tolerance rows
     // scalars, replicated in every thread (all derived from CTA-wide reductions, hence identical)
     double t_old, t_now, t_end, t_start, step, step_size, min_step, dir_inf, t_last;
     unsigned size, steps, nrej, nfev, len_t, te_old;
@@ -155,7 +156,7 @@ struct CtaSolver {
             double part = 0.0;
             for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
                 const double e = dot_k<ERow, NK>(i, ERow{});
-                const double sc = e / (p.atol[i] + fmax(fabs(y_old[i]), fabs(y_now[i])) * p.rtol[i]);
+                const double sc = e / (atolp[i] + fmax(fabs(y_old[i]), fabs(y_now[i])) * rtolp[i]);
                 part += (sc * sc);
             }
             const double norm = cta_sum(part, red);
@@ -163,7 +164,7 @@ struct CtaSolver {
         } else {
             double p3 = 0.0, p5 = 0.0;
             for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-                const double scale_inv = 1.0 / (p.atol[i] + fmax(fabs(y_old[i]), fabs(y_now[i])) * p.rtol[i]);
+                const double scale_inv = 1.0 / (atolp[i] + fmax(fabs(y_old[i]), fabs(y_now[i])) * rtolp[i]);
                 const double e3 = scale_inv * dot_k<E3Row, NS>(i, E3Row{});
                 const double e5 = scale_inv * dot_k<E5Row, NS>(i, E5Row{});
                 p3 += (e3 * e3);
@@ -193,7 +194,7 @@ struct CtaSolver {
         double* y_now = vecp(V_YNOW);
         double a = 0.0, b = 0.0;
         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-            const double scale = p.atol[i] + fabs(y_old[i]) * p.rtol[i];
+            const double scale = atolp[i] + fabs(y_old[i]) * rtolp[i];
             const double a0 = y_old[i] / scale;
             const double a1 = K(0)[i] / scale;
             a += (a0 * a0);
@@ -211,7 +212,7 @@ struct CtaSolver {
         eval_rhs(t_now, y_now, K(1));           // scratch use of K_1: overwritten by the first attempt
         double c = 0.0;
         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-            const double scale = p.atol[i] + fabs(y_old[i]) * p.rtol[i];
+            const double scale = atolp[i] + fabs(y_old[i]) * rtolp[i];
             const double a2 = (K(1)[i] - K(0)[i]) / scale;
             c += (a2 * a2);
         }
@@ -299,6 +300,8 @@ struct CtaSolver {
         fwd = (t_end - t_start) >= 0.0;
         dir_inf = fwd ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double((long long)0xfff0000000000000ULL);
         args = p.args + traj * p.args_stride;
+        rtolp = p.rtol + traj * p.tol_stride;              // (stride 0: one tolerance set for the batch)
+        atolp = p.atol + traj * p.tol_stride;
         size = steps = nrej = nfev = len_t = 0;
         status = ST_NO_ERROR; error_flag = false; te_finished = false;
         t_old = t_now = t_start; step = 0.0; step_size = 0.0;
@@ -362,9 +365,10 @@ struct CtaSolver {
             if (p.n_t_eval > 0 && !te_finished) {
                 do_save = false;
                 unsigned lo = 0, hi = p.n_t_eval;
-                while (lo < hi) { const unsigned m = (lo + hi) >> 1; if (p.t_eval[m] < t_now) lo = m + 1; else hi = m; }
+                const double* tev = p.t_eval + traj * p.t_eval_stride;
+                while (lo < hi) { const unsigned m = (lo + hi) >> 1; if (tev[m] < t_now) lo = m + 1; else hi = m; }
                 unsigned up = lo;
-                while (up < p.n_t_eval && !(t_now < p.t_eval[up])) up++;
+                while (up < p.n_t_eval && !(t_now < tev[up])) up++;
                 unsigned idx_new;
                 if (lo == up) idx_new = lo;
                 else if (fwd) { idx_new = up; if (idx_new == p.n_t_eval) te_finished = true; }
@@ -393,7 +397,7 @@ struct CtaSolver {
                         __syncthreads();
                     }
                     for (unsigned q = 0; q < delta; q++) {
-                        const double ti = fwd ? p.t_eval[te_old + q] : p.t_eval[te_old - q - 1];
+                        const double ti = fwd ? tev[te_old + q] : tev[te_old - q - 1];
                         const double x = (ti - t_old) / h;
                         // interpolate straight into the output row
                         if (p.t_rows != nullptr && size < p.row_cap) {

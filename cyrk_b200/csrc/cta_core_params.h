@@ -16,6 +16,7 @@ struct CtaParams {
     unsigned      t_span_stride;
     const double* rtol;          // [n]  (floored at 100 eps on the host)
     const double* atol;          // [n]
+    unsigned tol_stride;         // 0: one tolerance set for the batch; n: rtol / atol hold one row of n entries per trajectory
     int    uniform_tol;          // every component has the same tolerances (rtol0, atol0): no array reads
     double rtol0, atol0;
     double max_step, first_step;
@@ -23,6 +24,7 @@ struct CtaParams {
     int    user_max_steps;
     const double* t_eval;        // ascending (reversed copy for backward runs)
     unsigned n_t_eval;
+    unsigned t_eval_stride;      // 0: one t_eval for the batch; n_t_eval: one row per trajectory
     int*      status;
     unsigned* size;
     unsigned* steps_taken;

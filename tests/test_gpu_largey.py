@@ -275,3 +275,60 @@ def test_cta_events_match_oracle(oracle, method, n):
             assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
             assert np.all(np.abs(v.y - ref.y) <= _tol(ref.y, 1e-6, 1e-8))
         r.close()
+
+
+@pytest.mark.parametrize("n,kernel", [(96, 0), (700, 0), (5000, 0), (300, 1)], ids=["n96", "n700", "n5000", "n300-kernel-forced"])
+def test_cta_per_trajectory_tolerances_and_t_eval(oracle, n, kernel):
+    """SURVEY 8b row 1 on the CTA-per-trajectory path: one (rtol, atol) row and one t_eval row per trajectory, each trajectory
+    against ITS OWN oracle solve; both CTA kernels; forward and backward runs."""
+    rng = np.random.default_rng(41 + n)
+    B, m = 5, 7
+    y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, (B, n)))
+    args = np.stack([rng.uniform(-0.6, -0.4, B), np.full(B, float(n))], 1)
+    rt = 10.0 ** rng.uniform(-8, -5, (B, 1)) * np.where(np.arange(n) % 3 == 0, 0.5, 1.0)[None, :]     # (B, n): rows differ, components too
+    at = rt * 1e-2
+    c.lib().cyrk_b200_set_option(b"cta_kernel", kernel)
+    try:
+        # per-trajectory tolerances, raw step rows
+        r = c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method="RK45", args=args, rtol=rt, atol=at)
+        for i in range(B):
+            ref = oracle.solve("largey", (0.0, 10.0), y0[i], "RK45", rt[i], at[i], args=args[i])
+            v = r[i]
+            assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken), (n, i)
+            assert int(r.nfev[i]) == ref.nfev
+            assert np.allclose(v.t, ref.t, rtol=1e-6, atol=1e-12)
+            assert np.all(np.abs(v.y - ref.y) <= 10 * rt[i][:, None] * np.abs(ref.y) + 10 * at[i][:, None])
+        assert len(set(int(s) for s in r.steps_taken)) > 1          # the rows really were used per trajectory
+        # (B, 1) tolerances broadcast over the components == the same scalar pair per trajectory
+        r1 = c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method="RK23", args=args, rtol=rt[:, :1] * 100, atol=at[:, :1] * 100, store="final")
+        for i in range(B):
+            ref = oracle.solve("largey", (0.0, 10.0), y0[i], "RK23", float(rt[i, 0] * 100), float(at[i, 0] * 100), args=args[i])
+            assert (int(r1.status[i]), int(r1.steps_taken[i]), int(r1.nfev[i])) == (ref.status, ref.steps_taken, ref.nfev)
+        # per-trajectory t_eval (with per-trajectory tolerances on top), forward and backward
+        for span in ((0.0, 10.0), (10.0, 0.0)):
+            lo = rng.uniform(-0.5, 3.0, B); hi = rng.uniform(6.0, 10.0, B)
+            te = lo[:, None] + (hi - lo)[:, None] * np.sort(rng.uniform(0, 1, (B, m)), axis=1)
+            te[0, -1] = 10.0
+            if span[0] > span[1]:
+                te = te[:, ::-1].copy()
+            r2 = c.cysolve_ivp_batch("largey", span, y0, method="RK45", args=args, rtol=rt, atol=at, t_eval=te)
+            for i in range(B):
+                ref = oracle.solve("largey", span, y0[i], "RK45", rt[i], at[i], args=args[i], t_eval=te[i])
+                v = r2[i]
+                assert (v.status, v.size, v.steps_taken) == (ref.status, ref.size, ref.steps_taken), (n, span, i)
+                assert np.array_equal(v.t, ref.t)
+                assert np.all(np.abs(v.y - ref.y) <= 10 * rt[i][:, None] * np.abs(ref.y) + 10 * at[i][:, None])
+    finally:
+        c.lib().cyrk_b200_set_option(b"cta_kernel", 0)
+    # a shared row passed per trajectory is the shared solve of the same kernel, bit for bit (per-trajectory rows run on the
+    # shared-memory/slab kernel: option cta_kernel = 1 selects it for the shared solve too)
+    c.lib().cyrk_b200_set_option(b"cta_kernel", 1)
+    try:
+        a = c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method="RK45", args=args, rtol=rt[0], atol=at[0], store="final")
+    finally:
+        c.lib().cyrk_b200_set_option(b"cta_kernel", 0)
+    b = c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method="RK45", args=args, rtol=np.tile(rt[0], (B, 1)), atol=np.tile(at[0], (B, 1)), store="final")
+    for name in ("status", "steps_taken", "n_rejected", "nfev", "y_last"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    with pytest.raises(c.CyrkB200Error, match="cannot be combined"):
+        c.cysolve_ivp_batch("largey", (0.0, 10.0), y0, method="RK45", args=args, rtol=rt, atol=at, events=[c.Event("y0")])
