@@ -78,8 +78,10 @@ extern "C" {
 #define CYRK_FLAG_STRICT_FP   1u  /* kernels compiled with -fmad=false: reference's rounding (no FMA) */
 #define CYRK_FLAG_DEVICE_IO   2u  /* y0/args/t_span are DEVICE pointers; results stay on the device   */
 #define CYRK_FLAG_T_EVAL_PER_TRAJ 4u /* t_eval holds n_traj rows of n_t_eval sample times (one row per trajectory) */
-#define CYRK_FLAG_TOL_PER_TRAJ    8u /* rtols / atols hold n_traj rows of n_y entries (n_rtols == n_atols == n_traj * n_y);
-                                        thread-per-trajectory path; the kernels of this option are compiled on first use */
+#define CYRK_FLAG_TOL_PER_TRAJ    8u /* rtols / atols hold n_traj rows of n_y entries (n_rtols == n_atols == n_traj * n_y).
+                                        Thread-per-trajectory path: the kernels of this option are compiled on first use;
+                                        CTA-per-trajectory path (both per-trajectory flags): raw step rows / t_eval / final
+                                        state, not together with events or stored dense output */
 
 #define CYRK_EVENT_NO_LIMIT ((size_t)-1)   /* Event::max_allowed default, c_events.hpp:33 */
 
