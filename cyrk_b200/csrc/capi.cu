@@ -96,8 +96,10 @@ static int g_opt_cta2_large = 1;      // register-resident CTA kernel for 4096 <
 static int g_opt_cta_smem_vecs = -1;  // CTA path: working vectors kept in shared memory (-1 = as many as fit)
 static int g_opt_cta_block = 0;       // CTA path: threads per CTA (0 = by n_y)
 static int g_opt_pipe_taper = 1;       // pipelined host-I/O path: short first / last chunks
-static int g_opt_pipe_chunk = 1 << 21; // pipelined host-I/O path: trajectories per chunk (at most 32 chunks, at least 4).  2 Mi since the start-up
-                                       // kernel runs from 256 Ki: 8 Mi LV trajectories end to end 19.33 ms against 20.02 with 1 Mi (profiles/r02_e2e_pipe_chunk.log)
+static int g_opt_pipe_chunk = 3 << 20; // pipelined host-I/O path: largest body chunk (trajectories).  Larger chunks run the persistent grid better,
+                                       // smaller ones overlap more of the copies: 8 Mi LV trajectories end to end 20.02 ms (1 Mi) / 19.35 (2 Mi) /
+                                       // 19.20 (3 - 4 Mi) (profiles/r02_e2e_pipe_chunk.log, r02_s9_e2e_sched.log)
+static int g_opt_pipe_sched = 1;       // pipelined host-I/O path: 1 = head / body / tail schedule, 0 = equal chunks with tapered ends (round 2, first half)
 static int g_opt_pipe_min = 1 << 18;   // pipelined host-I/O path: smallest batch that takes it (0 = never)
 static int g_opt_cta_kernel = 0;      // CTA path: 0 = pick (register-resident kernel where it is faster), 1 = always the
                                       // shared-memory/slab kernel, 2 = the register-resident kernel whenever n_y <= 4096
@@ -473,7 +475,27 @@ static int solve_lean_pipelined(Handle* h, const SolveArgs& a, const Dispatch* p
     // a 256 Ki ... 2 Mi batch still overlaps its copies with the solve; never more than 32 chunks
     const size_t chunk = std::max<size_t>(std::min<size_t>((size_t)g_opt_pipe_chunk, ((B + 3) / 4 + 1023) / 1024 * 1024), (B + 31) / 32);
     std::vector<std::pair<size_t, size_t>> sched;          // (offset, count)
-    {
+    if (g_opt_pipe_sched == 1) {
+        // Head / body / tail: what the copies want (a SHORT first chunk: its copy-in overlaps nothing; short last chunks: the
+        // last copy-out overlaps nothing) is decoupled from what the solve wants (FEW, LARGE chunks: a chunk of 256 Ki runs
+        // the persistent grid at 1.7 trajectories per lane).  head = B/16 in [32 Ki, 512 Ki]; tail = 2 head + head; the body is
+        // cut into equal parts of at most pipe_chunk.
+        size_t off = 0;
+        auto push = [&](size_t n) { n = std::min(n, B - off); if (n) { sched.emplace_back(off, n); off += n; } };
+        const size_t head_min = std::min<size_t>((size_t)32 << 10, (size_t)g_opt_pipe_chunk);
+        const size_t head = std::min<size_t>(std::max<size_t>(((B / 16) + 1023) / 1024 * 1024, head_min), (size_t)512 << 10);
+        if (B <= 4 * head) push(B);
+        else {
+            const size_t body = B - 4 * head;
+            const size_t parts = (body + (size_t)g_opt_pipe_chunk - 1) / (size_t)g_opt_pipe_chunk;
+            const size_t part = ((body + parts - 1) / parts + 1023) / 1024 * 1024;
+            push(head);
+            while (B - off > 3 * head + part) push(part);
+            push(B - off - 3 * head);
+            push(2 * head);
+            push(head);
+        }
+    } else {
         size_t off = 0;
         auto push = [&](size_t n) { n = std::min(n, B - off); if (n) { sched.emplace_back(off, n); off += n; } };
         const bool taper = g_opt_pipe_taper && B >= 4 * chunk;
@@ -2339,6 +2361,7 @@ int cyrk_b200_set_option(const char* name, int value)
     if (!strcmp(name, "cta_block")) { g_opt_cta_block = value; return 0; }
     if (!strcmp(name, "cta_kernel")) { g_opt_cta_kernel = value; return 0; }
     if (!strcmp(name, "pipe_taper")) { g_opt_pipe_taper = value; return 0; }
+    if (!strcmp(name, "pipe_sched")) { g_opt_pipe_sched = value; return 0; }
     if (!strcmp(name, "pipe_min")) { g_opt_pipe_min = value; return 0; }
     if (!strcmp(name, "pipe_chunk")) { if (value < 1024) { set_error("pipe_chunk must be >= 1024"); return -1; } g_opt_pipe_chunk = value; return 0; }
     set_error("unknown option '%s'", name);

@@ -271,7 +271,7 @@ size_t   cyrk_b200_get_lazy_d2h_bytes(void* h); /* copied afterwards by getters 
 /* Tuning knobs (process-wide): "refill_min" (1..32), "block" (threads per CTA of the thread-per-trajectory kernels,
  * 0 = by occupancy), "ctas_per_sm" (0 = occupancy API), "prep" (start-up kernel: -1 auto / 0 / 1), "root_batch" (1..32),
  * "cta_kernel" (0 = register-resident CTA kernel where it applies, 1 = shared-memory/slab kernel), "cta_block",
- * "cta_smem_vecs" (slab kernel only), "cta2_large" (1 = register-resident kernel also for 4096 < n_y <= 12288), "pipe_chunk" (trajectories per chunk of the pipelined host-I/O path),
+ * "cta_smem_vecs" (slab kernel only), "cta2_large" (1 = register-resident kernel also for 4096 < n_y <= 12288), "pipe_chunk" (largest body chunk of the pipelined host-I/O path, trajectories), "pipe_sched" (1 = head / body / tail schedule, 0 = equal chunks),
  * "pipe_taper" (short first/last chunks, 0/1), "pipe_min" (smallest host-buffer final-state batch that takes the pipelined path;
  * default 256 Ki, 0 = never), "two_pass" (dense_output / t_eval without events or extras: 1 = step-parallel
  * interpolants when dense_output is set [default], 2 = also for t_eval alone, 0 = always the per-trajectory kernel; the

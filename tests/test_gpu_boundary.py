@@ -71,7 +71,7 @@ def test_per_trajectory_tolerances_through_the_pipelined_and_streamed_paths():
         b_rows = c.cysolve_ivp_batch("lotkavolterra", (0.0, 10.0), y0, store="rows", expected_size=512, **kw)
         assert b_rows.launches > a_rows.launches
     finally:
-        _opt("pipe_min", 1 << 18); _opt("pipe_chunk", 1 << 21); _opt("stream", 1); _opt("stream_chunk", 0)
+        _opt("pipe_min", 1 << 18); _opt("pipe_chunk", 3 << 20); _opt("stream", 1); _opt("stream_chunk", 0)
     for a, b in ((a_final, b_final), (a_rows, b_rows)):
         for name in ("status", "size", "steps_taken", "n_rejected", "nfev", "t_last", "y_last"):
             assert np.array_equal(getattr(a, name), getattr(b, name)), name
