@@ -61,3 +61,27 @@ def test_port_vs_reference_random_batch(oracle):
     c = oracle.solve_batch(impl="ref", n_threads=4, **kw)
     for k in ("status", "size", "steps", "nfev", "t_last", "y_last"):
         assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k])
+
+
+@pytest.mark.parametrize("n", [96, 700])
+def test_port_matches_reference_largey_tolerance_arrays_and_t_eval(oracle, n):
+    """What tests/test_gpu_largey.py::test_cta_per_trajectory_tolerances_and_t_eval leans on: the port equals the compiled
+    reference bit for bit for a large system with per-component rtol / atol arrays, with and without t_eval, forward and
+    backward (the reversed-t_eval copy of cysolver.cpp:520-527)."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built on this box")
+    rng = np.random.default_rng(7 + n)
+    y0 = 100.0 * (1 + 0.01 * rng.uniform(-1, 1, n))
+    rt = 10.0 ** rng.uniform(-8, -5) * np.where(np.arange(n) % 3 == 0, 0.5, 1.0)
+    at = rt * 1e-2
+    args = [-0.47, float(n)]
+    for span in ((0.0, 10.0), (10.0, 0.0)):
+        te = np.sort(rng.uniform(-0.5, 10.0, 7))
+        te[-1] = 10.0
+        if span[0] > span[1]:
+            te = te[::-1].copy()
+        for t_eval in (None, te):
+            a = oracle.solve("largey", span, y0, "RK45", rt, at, args=args, t_eval=t_eval, impl="ref")
+            b = oracle.solve("largey", span, y0, "RK45", rt, at, args=args, t_eval=t_eval, impl="port")
+            assert (a.status, a.size, a.steps_taken, a.nfev) == (b.status, b.size, b.steps_taken, b.nfev), (n, span)
+            assert np.array_equal(a.t, b.t) and np.array_equal(a.y, b.y, equal_nan=True)
